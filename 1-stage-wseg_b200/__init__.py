@@ -1,0 +1,17 @@
+"""B200-native PAMR + pseudo-label epilogue (drop-in for the hot path of EnchanterXiao/1-stage-wseg).
+
+The directory name `1-stage-wseg_b200` is not a Python identifier; import it as `wseg_b200`
+(the alias module at the repository root registers this package under that name).
+"""
+from . import _lib
+from .pamr import PAMR, LocalAffinity, LocalAffinityAbs, LocalAffinityCopy, LocalStDev
+from .pamr import local_affinity, propagate, resize_bilinear
+from .stage import (IGNORE_INDEX, labels_from_pseudo_gt, pseudo_gtmask, pseudo_labels, refine_and_label,
+                    rescale_and_clean, run_pamr)
+from .dist import ShardedPseudoLabeler, gather_labels, shard_batch, shard_range
+
+__all__ = [
+    "PAMR", "LocalAffinity", "LocalAffinityAbs", "LocalAffinityCopy", "LocalStDev", "local_affinity", "propagate",
+    "resize_bilinear", "run_pamr", "rescale_and_clean", "pseudo_gtmask", "pseudo_labels", "labels_from_pseudo_gt",
+    "refine_and_label", "IGNORE_INDEX", "ShardedPseudoLabeler", "gather_labels", "shard_batch", "shard_range",
+]

@@ -1,0 +1,127 @@
+"""Pseudo-label epilogue of stage_net around PAMR, backed by libpamr_b200.so.
+
+Mirrors the helpers every reference model file carries (paths relative to the reference root):
+  run_pamr            models/SoftMaxAE.py:176-179   image -> mask size, then PAMR
+  _rescale_and_clean  models/SoftMaxAE.py:263-268   bilinear to the image size, masks[:,1:] *= labels
+  pseudo_gtmask       models/SoftMaxAE.py:29-50     per-class thresholds, ambiguity removal
+  argmax / ignore     models/SoftMaxAE.py:61-67     label map with 255 = ignore
+plus `pseudo_labels` / `refine_and_label`, the fused path that never materialises the
+up-sampled float tensors (what bench.py times as "PAMR + clean/argmax epilogue").
+"""
+import torch
+
+from . import _lib
+from .pamr import PAMR, _check_cuda_f32, _dev, _stream, resize_bilinear
+
+IGNORE_INDEX = 255
+
+
+def run_pamr(pamr, im, mask):
+    """run_pamr(self, im, mask) with self._aff == pamr (SoftMaxAE.py:176-179)."""
+    im = resize_bilinear(im, mask.shape[-2:]) if tuple(im.shape[-2:]) != tuple(mask.shape[-2:]) else im
+    return pamr(im, mask)
+
+
+def _labels_arg(labels, B, C, device):
+    if labels is None:
+        return None
+    labels = labels.detach().to(device=device, dtype=torch.float32).contiguous()
+    if tuple(labels.shape) != (B, C - 1):
+        raise RuntimeError("labels must have shape [B, C-1] = %s, got %s" % ((B, C - 1), tuple(labels.shape)))
+    return labels
+
+
+def _size_of(image_or_size):
+    if isinstance(image_or_size, torch.Tensor):
+        return int(image_or_size.shape[-2]), int(image_or_size.shape[-1])
+    return int(image_or_size[0]), int(image_or_size[1])
+
+
+def rescale_and_clean(masks, image, labels, return_class_max=False):
+    """_rescale_and_clean(self, masks, image, labels) (SoftMaxAE.py:263-268): returns a NEW tensor
+    [B,C,H,W]; `masks` is not modified.  `image` may be a tensor or an (H, W) pair."""
+    masks = _check_cuda_f32("masks", masks)
+    B, C, h, w = masks.shape
+    H, W = _size_of(image)
+    lab = _labels_arg(labels, B, C, masks.device)
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=masks.device)
+    cmax = torch.empty((B, C), dtype=torch.int32, device=masks.device) if return_class_max else None
+    _lib.check(_lib.lib().pamr_clean_f32(masks.data_ptr(), lab.data_ptr() if lab is not None else None, out.data_ptr(),
+                                         cmax.data_ptr() if cmax is not None else None, B, C, h, w, H, W, _dev(masks),
+                                         _stream(masks.device)))
+    return (out, cmax) if return_class_max else out
+
+
+def pseudo_labels(masks, labels=None, size=None, class_max=None, cutoff_top=0.6, cutoff_low=0.2, cutoff_bg=0.7,
+                  return_onehot=False, return_counts=False):
+    """Fused _rescale_and_clean -> pseudo_gtmask -> argmax/ignore (SoftMaxAE.py:263-268, 29-50, 61-67).
+
+    masks [B,C,h,w] (PAMR output, un-gated), labels [B,C-1] or None, size = target (H, W) or None.
+    class_max: the un-gated per-class max returned by PAMR.forward(..., return_class_max=True)
+    (only usable without a resize); otherwise it is computed here.
+    Returns uint8 labels [B,H,W] (255 = ignore) and, on request, the float one-hot pseudo_gt
+    [B,C,H,W] and int32 per-class pixel counts [B,C]."""
+    masks = _check_cuda_f32("masks", masks)
+    B, C, h, w = masks.shape
+    H, W = _size_of(size) if size is not None else (h, w)
+    lab = _labels_arg(labels, B, C, masks.device)
+    L = _lib.lib()
+    dev, st = _dev(masks), _stream(masks.device)
+    resize = (h, w) != (H, W)
+    gated = 1
+    if class_max is None or resize:
+        class_max = torch.empty((B, C), dtype=torch.int32, device=masks.device)
+        _lib.check(L.pamr_clean_f32(masks.data_ptr(), lab.data_ptr() if lab is not None else None, None,
+                                    class_max.data_ptr(), B, C, h, w, H, W, dev, st))
+    else:
+        gated = 0
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=masks.device)
+    onehot = torch.empty((B, C, H, W), dtype=torch.float32, device=masks.device) if return_onehot else None
+    counts = torch.empty((B, C), dtype=torch.int32, device=masks.device) if return_counts else None
+    _lib.check(L.pamr_pseudo_labels_f32(
+        masks.data_ptr(), lab.data_ptr() if lab is not None else None, class_max.data_ptr(), out.data_ptr(),
+        onehot.data_ptr() if onehot is not None else None, counts.data_ptr() if counts is not None else None, B, C, h, w,
+        H, W, float(cutoff_bg), float(cutoff_top), float(cutoff_low), gated, dev, st))
+    res = (out,)
+    if return_onehot:
+        res += (onehot,)
+    if return_counts:
+        res += (counts,)
+    return res if len(res) > 1 else out
+
+
+def pseudo_gtmask(mask, cutoff_top=0.6, cutoff_low=0.2, eps=1e-8):
+    """pseudo_gtmask(mask, cutoff_top, cutoff_low, eps) (SoftMaxAE.py:29-50): float one-hot-or-empty
+    [B,C,H,W].  (`eps` is unused in the reference as well.)"""
+    _, onehot = pseudo_labels(mask, None, None, None, cutoff_top, cutoff_low, 0.7, return_onehot=True)
+    return onehot
+
+
+def labels_from_pseudo_gt(pseudo_gt, ignore_index=IGNORE_INDEX):
+    """argmax + ignore (SoftMaxAE.py:61-67) for callers that hold a float pseudo_gt already."""
+    mask_gt = torch.argmax(pseudo_gt, 1)
+    mask_gt[pseudo_gt.sum(1) < 1.] = ignore_index
+    return mask_gt
+
+
+def refine_and_label(pamr, image_raw, masks, labels, out_size=None, return_masks=False, return_counts=False):
+    """Sequence A of stage_net (SoftMaxAE.py:250-259) in as few passes as possible:
+    run_pamr(image_raw, masks) -> _rescale_and_clean(., labels) -> pseudo_gtmask -> label map.
+
+    image_raw [B,K,Hi,Wi], masks [B,C,h,w] (softmax scores), labels [B,C-1].  out_size defaults
+    to the image size.  Returns uint8 labels [B,H,W]; with return_masks also the refined
+    (un-gated, mask-resolution) masks_dec."""
+    if not isinstance(pamr, PAMR):
+        raise TypeError("pamr must be a wseg_b200.PAMR module")
+    H, W = _size_of(out_size) if out_size is not None else _size_of(image_raw)
+    h, w = int(masks.shape[-2]), int(masks.shape[-1])
+    im = resize_bilinear(image_raw, (h, w)) if tuple(image_raw.shape[-2:]) != (h, w) else image_raw
+    if (h, w) == (H, W):
+        dec, cmax = pamr(im, masks, return_class_max=True)  # class max fused into the last iteration
+        res = pseudo_labels(dec, labels, None, cmax, return_counts=return_counts)
+    else:
+        dec = pamr(im, masks)
+        res = pseudo_labels(dec, labels, (H, W), None, return_counts=return_counts)
+    if not return_masks:
+        return res
+    return (res + (dec,)) if isinstance(res, tuple) else (res, dec)

@@ -1,0 +1,166 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol the header declares, the
+nn.Module mirrors the reference's state dict, the product never touches the oracle, and the
+batch-shard / gather logic works with world_size 2 on gloo.  No GPU compute is attempted."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import wseg_b200
+from wseg_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "1-stage-wseg_b200")
+D6 = [1, 2, 4, 8, 12, 24]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.lib()
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "pamr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pamr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = header_functions()
+    assert len(names) >= 12
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), "libpamr_b200.so does not export %s" % n
+        assert n in _lib.SIGNATURES, "ctypes binding lacks %s" % n
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.pamr_b200_abi_version() == _lib.ABI_VERSION
+
+
+def test_library_is_sm100a_only():
+    out = os.popen("cuobjdump -lelf %s 2>/dev/null" % _lib.LIB_PATH).read()
+    if not out.strip():
+        pytest.skip("cuobjdump not available")
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_ordered_encoding_monotone(lib):
+    vals = np.array([-np.inf, -3.5, -1e-30, -0.0, 0.0, 1e-30, 0.2, 0.7, 1.0, 3e38, np.inf], dtype=np.float32)
+    enc = [lib.pamr_ordered_from_float(float(v)) for v in vals]
+    assert all(a <= b for a, b in zip(enc, enc[1:]))
+    assert all(e > 0 for e in enc)
+    for v, e in zip(vals, enc):
+        assert lib.pamr_float_from_ordered(e) == v
+
+
+def test_no_gpu_means_error_not_fallback(lib):
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    x = np.zeros(16, dtype=np.float32)
+    rc = lib.pamr_resize_bilinear_f32(x.ctypes.data, x.ctypes.data, 1, 2, 2, 4, 4, 0, None)
+    assert rc != 0
+    assert len(lib.pamr_last_error()) > 0
+    with pytest.raises(RuntimeError):
+        _lib.check(rc)
+
+
+def test_cpu_tensors_raise():
+    m = wseg_b200.PAMR(10, D6)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 8, 8), torch.zeros(1, 2, 8, 8))
+    with pytest.raises(RuntimeError):
+        wseg_b200.pseudo_labels(torch.zeros(1, 3, 8, 8))
+
+
+def test_state_dict_matches_reference(golden_dir):
+    ref = np.load(os.path.join(golden_dir, "state_dict.npz"))
+    m = wseg_b200.PAMR(10, D6)
+    sd = m.state_dict()
+    assert list(sd.keys()) == ["aff_x.kernel", "aff_m.kernel", "aff_std.kernel"]
+    assert sorted(sd.keys()) == sorted(ref.files)
+    for k in ref.files:
+        assert tuple(sd[k].shape) == ref[k].shape
+        np.testing.assert_array_equal(sd[k].numpy(), ref[k])
+    assert len(list(m.parameters())) == 0
+    # reference attributes (pamr.py:119-122, :14)
+    assert m.num_iter == 10 and m.aff_x.dilations == D6 and m.aff_m.dilations == D6 and m.aff_std.dilations == D6
+    d = wseg_b200.PAMR()
+    assert d.num_iter == 1 and d.dilations == [1]
+
+
+def test_strict_load_and_tamper_check(golden_dir):
+    ref = np.load(os.path.join(golden_dir, "state_dict.npz"))
+    sd = {k: torch.from_numpy(ref[k]) for k in ref.files}
+    m = wseg_b200.PAMR(10, D6)
+    m.load_state_dict(sd, strict=True)
+    bad = {k: v.clone() for k, v in sd.items()}
+    bad["aff_m.kernel"][0, 0, 0, 0] = 0.5
+    with pytest.raises(AssertionError):
+        wseg_b200.PAMR(10, D6).load_state_dict(bad, strict=True)
+    # embedded in a parent module, keys get the parent's prefix like `_aff.aff_x.kernel`
+    parent = torch.nn.Module()
+    parent._aff = wseg_b200.PAMR(10, D6)
+    assert sorted(parent.state_dict()) == ["_aff.aff_m.kernel", "_aff.aff_std.kernel", "_aff.aff_x.kernel"]
+
+
+def test_product_never_touches_oracle():
+    files = glob.glob(os.path.join(PKG, "**", "*.py"), recursive=True) + \
+        glob.glob(os.path.join(PKG, "csrc", "*.cu*")) + [os.path.join(ROOT, "include", "pamr_b200.h")]
+    assert len(files) > 8
+    for f in files:
+        assert "oracle" not in open(f).read().lower(), f
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(PKG, "does_not_exist.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_shard_range_partitions():
+    for B in (1, 7, 16, 128):
+        for world in (1, 2, 3, 4, 8):
+            spans = [wseg_b200.shard_range(B, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        wseg_b200.shard_range(4, 2, 2)
+
+
+def _gather_worker(rank, world, port, batch, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = (torch.arange(batch * 3 * 5, dtype=torch.int64) % 251).to(torch.uint8).view(batch, 3, 5)
+        local = wseg_b200.shard_batch(full, rank, world).clone()
+        out = wseg_b200.gather_labels(local, batch)
+        q.put((rank, bool(torch.equal(out, full))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [4, 5])
+def test_gather_labels_gloo_world2(batch):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + batch
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, batch, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]

@@ -142,28 +142,54 @@ int pamr_affinity_f32(const float* img, float* aff, int B, int K, int H, int W, 
     PAMR_TRY(check_dims(B, K, H, W));
     Dilations dil;
     PAMR_TRY(make_dilations(dilations, nd, &dil));
-    return launch_affinity(img, aff, B, K, H, W, dil, (cudaStream_t)stream);
+    return launch_affinity(img, aff, B, K, H, W, dil, AffTiling{0, 0, 0}, (cudaStream_t)stream);
 }
 
-int pamr_propagate_f32(const float* aff, const float* m_in, float* m_out, float* m_tmp, int B, int C, int H, int W,
-                       const int* dilations, int nd, int iters, unsigned* cls_max, int dev, pamr_stream_t stream) {
+size_t pamr_propagate_scratch_bytes(int B, int C, int H, int W, const int* dilations, int nd, int iters) {
+    Dilations dil;
+    if (make_dilations(dilations, nd, &dil) != PAMR_OK) return 0;
+    return propagate_scratch_bytes(B, C, H, W, dil, iters, false);
+}
+
+int pamr_propagate_f32(const float* aff, const float* m_in, float* m_out, void* scratch, size_t scratch_bytes, int B,
+                       int C, int H, int W, const int* dilations, int nd, int iters, unsigned* cls_max, int dev,
+                       pamr_stream_t stream) {
     PAMR_ENTER(dev);
     PAMR_REQUIRE(aff && m_in && m_out, "propagate: NULL pointer");
     PAMR_REQUIRE(iters >= 0, "propagate: iters=%d is negative", iters);
-    PAMR_REQUIRE(m_in != m_out && m_in != m_tmp && m_out != m_tmp, "propagate: m_in, m_out, m_tmp must not alias");
+    PAMR_REQUIRE(m_in != m_out, "propagate: m_in and m_out must not alias");
     PAMR_TRY(check_dims(B, C, H, W));
     Dilations dil;
     PAMR_TRY(make_dilations(dilations, nd, &dil));
-    return launch_propagate(aff, m_in, m_out, m_tmp, B, C, H, W, dil, iters, cls_max, dev, (cudaStream_t)stream);
+    return launch_propagate(aff, false, m_in, m_out, scratch, scratch_bytes, B, C, H, W, dil, iters, cls_max, dev,
+                            (cudaStream_t)stream);
 }
 
-size_t pamr_forward_workspace_bytes(int B, int K, int C, int H, int W, int h, int w, int nd, int iters) {
-    (void)K;
+namespace {
+// workspace carve-up shared by pamr_forward_workspace_bytes and pamr_forward_f32
+struct ForwardPlan {
+    AffTiling tiling;
+    size_t aff_bytes, scratch_bytes, resize_bytes, total;
+};
+ForwardPlan plan_forward(int B, int C, int H, int W, int h, int w, const Dilations& dil, int iters) {
+    ForwardPlan p;
     const size_t HW = (size_t)H * W;
-    size_t bytes = align_up(sizeof(float) * (size_t)B * 8 * nd * HW, 256);         // affinity
-    if (iters > 1) bytes += align_up(sizeof(float) * (size_t)B * C * HW, 256);     // ping-pong buffer
-    if (h != H || w != W) bytes += align_up(sizeof(float) * (size_t)B * C * HW, 256);  // resized mask
-    return bytes;
+    p.tiling = tuned_tiling(H, W, dil);
+    const size_t aff_floats = p.tiling.R > 0 ? aff_tiled_floats(B, p.tiling) : (size_t)B * 8 * dil.nd * HW;
+    p.aff_bytes = align_up(sizeof(float) * aff_floats, 256);
+    p.scratch_bytes = align_up(propagate_scratch_bytes(B, C, H, W, dil, iters, p.tiling.R > 0), 256);
+    p.resize_bytes = (h != H || w != W) ? align_up(sizeof(float) * (size_t)B * C * HW, 256) : 0;
+    p.total = p.aff_bytes + p.scratch_bytes + p.resize_bytes;
+    return p;
+}
+}  // namespace
+
+size_t pamr_forward_workspace_bytes(int B, int K, int C, int H, int W, int h, int w, const int* dilations, int nd,
+                                    int iters) {
+    (void)K;
+    Dilations dil;
+    if (make_dilations(dilations, nd, &dil) != PAMR_OK) return 0;
+    return plan_forward(B, C, H, W, h, w, dil, iters).total;
 }
 
 int pamr_forward_f32(const float* img, const float* mask, float* out, void* workspace, size_t workspace_bytes, int B,
@@ -176,28 +202,24 @@ int pamr_forward_f32(const float* img, const float* mask, float* out, void* work
     PAMR_TRY(check_dims(B, C, H, W));
     Dilations dil;
     PAMR_TRY(make_dilations(dilations, nd, &dil));
-    const size_t need = pamr_forward_workspace_bytes(B, K, C, H, W, h, w, nd, iters);
-    if (workspace == nullptr || workspace_bytes < need)
-        return set_error(PAMR_ERR_WORKSPACE, "forward: workspace of %zu bytes given, %zu needed", workspace_bytes, need);
+    const ForwardPlan plan = plan_forward(B, C, H, W, h, w, dil, iters);
+    if (workspace == nullptr || workspace_bytes < plan.total)
+        return set_error(PAMR_ERR_WORKSPACE, "forward: workspace of %zu bytes given, %zu needed", workspace_bytes,
+                         plan.total);
     PAMR_REQUIRE(((uintptr_t)workspace & 255) == 0, "forward: workspace must be 256-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t HW = (size_t)H * W;
     char* ws = (char*)workspace;
     float* aff = (float*)ws;
-    ws += align_up(sizeof(float) * (size_t)B * 8 * nd * HW, 256);
-    float* tmp = nullptr;
-    if (iters > 1) {
-        tmp = (float*)ws;
-        ws += align_up(sizeof(float) * (size_t)B * C * HW, 256);
-    }
+    void* scratch = ws + plan.aff_bytes;
     const float* m0 = mask;
     if (h != H || w != W) {
-        float* rs = (float*)ws;
+        float* rs = (float*)(ws + plan.aff_bytes + plan.scratch_bytes);
         PAMR_TRY(launch_resize_bilinear(mask, rs, B * C, h, w, H, W, s));  // pamr.py:125
         m0 = rs;
     }
-    PAMR_TRY(launch_affinity(img, aff, B, K, H, W, dil, s));                                       // pamr.py:132-136
-    return launch_propagate(aff, m0, out, tmp, B, C, H, W, dil, iters, cls_max, dev, s);           // pamr.py:138-140
+    PAMR_TRY(launch_affinity(img, aff, B, K, H, W, dil, plan.tiling, s));  // pamr.py:132-136
+    return launch_propagate(aff, plan.tiling.R > 0, m0, out, scratch, plan.scratch_bytes, B, C, H, W, dil, iters, cls_max,
+                            dev, s);  // pamr.py:138-140
 }
 
 int pamr_clean_f32(const float* m, const float* labels, float* cleaned, unsigned* cls_max, int B, int C, int h, int w,
@@ -237,14 +259,17 @@ int pamr_pseudo_labels_host_f32(const float* h_img, const float* h_mask, const f
     const size_t HW = (size_t)H * W, hw = (size_t)h * w;
     const size_t n_img = sizeof(float) * (size_t)B * K * HW, n_ims = sizeof(float) * (size_t)B * K * hw;
     const size_t n_mask = sizeof(float) * (size_t)B * C * hw, n_lab = sizeof(float) * (size_t)B * (C - 1);
-    const size_t n_aff = sizeof(float) * (size_t)B * 8 * nd * hw, n_out = (size_t)B * HW;
+    const AffTiling tiling = tuned_tiling(h, w, dil);
+    const size_t n_aff = sizeof(float) * (tiling.R > 0 ? aff_tiled_floats(B, tiling) : (size_t)B * 8 * nd * hw);
+    const size_t n_out = (size_t)B * HW;
     const size_t n_max = sizeof(unsigned) * (size_t)B * C;
     const bool resize = (h != H || w != W);
     // one allocation, carved up
     size_t off = 0;
     auto carve = [&](size_t n) { size_t o = off; off += align_up(n ? n : 1, 256); return o; };
     const size_t o_img = carve(n_img), o_ims = carve(resize ? n_ims : 0), o_mask = carve(n_mask);
-    const size_t o_lab = carve(n_lab), o_aff = carve(n_aff), o_a = carve(n_mask), o_b = carve(n_mask);
+    const size_t n_scr = propagate_scratch_bytes(B, C, h, w, dil, iters, tiling.R > 0);
+    const size_t o_lab = carve(n_lab), o_aff = carve(n_aff), o_a = carve(n_mask), o_b = carve(n_scr);
     const size_t o_max = carve(n_max), o_out = carve(n_out);
     char* d = nullptr;
     cudaStream_t s = nullptr;
@@ -264,10 +289,10 @@ int pamr_pseudo_labels_host_f32(const float* h_img, const float* h_mask, const f
             PAMR_TRY(launch_resize_bilinear(im, (float*)(d + o_ims), B * K, H, W, h, w, s));
             im = (const float*)(d + o_ims);
         }
-        PAMR_TRY(launch_affinity(im, (float*)(d + o_aff), B, K, h, w, dil, s));
+        PAMR_TRY(launch_affinity(im, (float*)(d + o_aff), B, K, h, w, dil, tiling, s));
         unsigned* mx = (unsigned*)(d + o_max);
-        PAMR_TRY(launch_propagate((const float*)(d + o_aff), (const float*)(d + o_mask), (float*)(d + o_a),
-                                  (float*)(d + o_b), B, C, h, w, dil, iters, resize ? nullptr : mx, dev, s));
+        PAMR_TRY(launch_propagate((const float*)(d + o_aff), tiling.R > 0, (const float*)(d + o_mask), (float*)(d + o_a), d + o_b,
+                                  n_scr, B, C, h, w, dil, iters, resize ? nullptr : mx, dev, s));
         const float* lab = (h_labels && C > 1) ? (const float*)(d + o_lab) : nullptr;
         if (resize) PAMR_TRY(launch_clean((const float*)(d + o_a), lab, nullptr, mx, B, C, h, w, H, W, s));
         PAMR_TRY(launch_pseudo_labels((const float*)(d + o_a), lab, mx, (uint8_t*)(d + o_out), nullptr, nullptr, B, C, h,

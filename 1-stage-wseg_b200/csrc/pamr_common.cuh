@@ -23,6 +23,42 @@ __device__ __forceinline__ int tap_dx(int j) {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+// ---- tile-major affinity layout consumed by the tuned sm_100a propagation kernel ----
+// Only for the standard 6 dilations (48 taps).  The tuned kernel's thread (lane quarter wq, lane)
+// of tile (ty,tx) owns R pixels (rows ty*4R + wq*R + i, column tx*32 + lane) and parks its 48*R
+// weights in TMEM in the "sequence" order s below, so the affinity kernel writes them as
+//   [b][ty][tx][wq][s][i][lane]           (each [s][i] row = 32 lanes = one 128-byte line)
+// which makes the TMEM fill a stream of coalesced loads at immediate offsets from one pointer.
+// Pixels of partial tiles that lie outside the image hold zeros.
+//
+// Tap sequence s (0..47) <-> reference tap p = 8*id + j (pamr.py:25-34):
+//   s <  12: centre column (b = 0): id = s/2, j = 1 (dy=-d) or 6 (dy=+d)
+//   s >= 12: side group g = (s-12)/3 = 6*bi + id (bi = 0: dx=-d, bi = 1: dx=+d), a = (s-12)%3 -> dy = (a-1)*d
+__host__ __device__ constexpr int seq_tap(int s) {
+    if (s < 12) return 8 * (s / 2) + ((s % 2 == 0) ? 1 : 6);
+    const int t = s - 12, g = t / 3, a = t % 3, bi = g / 6, id = g % 6;
+    const int j = (bi == 0) ? (a == 0 ? 0 : a == 1 ? 3 : 5) : (a == 0 ? 2 : a == 1 ? 4 : 7);
+    return 8 * id + j;
+}
+__host__ __device__ constexpr int tap_seq(int p) {
+    const int id = p / 8, j = p % 8;
+    if (j == 1) return 2 * id;
+    if (j == 6) return 2 * id + 1;
+    const int bi = (j == 0 || j == 3 || j == 5) ? 0 : 1;
+    const int a = (j == 0 || j == 2) ? 0 : (j == 3 || j == 4) ? 1 : 2;
+    return 12 + (bi * 6 + id) * 3 + a;
+}
+struct AffTiling {
+    int R, tiles_x, tiles_y;  // R rows per thread (tile = 32 x 4R); R == 0: standard [B,48,H,W] layout
+};
+__host__ __device__ __forceinline__ size_t aff_tiled_floats(int B, const AffTiling& t) {
+    return (size_t)B * t.tiles_y * t.tiles_x * 4 * 48 * t.R * 32;
+}
+__host__ __device__ __forceinline__ size_t aff_tiled_index(const AffTiling& t, int b, int s, int y, int x) {
+    const int ty = y / (4 * t.R), ry = y % (4 * t.R), wq = ry / t.R, i = ry % t.R;
+    return ((((((size_t)b * t.tiles_y + ty) * t.tiles_x + (x >> 5)) * 4 + wq) * 48 + s) * t.R + i) * 32 + (x & 31);
+}
+
 // Monotone float <-> unsigned map so that atomicMax(unsigned) implements a float max for any sign.
 __host__ __device__ __forceinline__ unsigned ordered_from_float(float v) {
 #ifdef __CUDA_ARCH__
@@ -60,9 +96,16 @@ void count_launch(int n = 1);
 
 // Kernel launchers implemented in the .cu files (all enqueue on `s`, return a PAMR_* code).
 int launch_resize_bilinear(const float* src, float* dst, int n_planes, int h, int w, int H, int W, cudaStream_t s);
-int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, const Dilations& dil, cudaStream_t s);
-int launch_propagate(const float* aff, const float* m_in, float* m_out, float* m_tmp, int B, int C, int H, int W,
-                     const Dilations& dil, int iters, unsigned* cls_max, int dev, cudaStream_t s);
+int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, const Dilations& dil,
+                    const AffTiling& tiling, cudaStream_t s);
+int launch_aff_relayout(const float* aff_std, float* aff_tiled, int B, int H, int W, const AffTiling& tiling,
+                        cudaStream_t s);
+// Tiling of the tuned propagation kernel for this problem; R == 0 when only the generic kernel applies.
+AffTiling tuned_tiling(int H, int W, const Dilations& dil);
+size_t propagate_scratch_bytes(int B, int C, int H, int W, const Dilations& dil, int iters, bool aff_is_tiled);
+int launch_propagate(const float* aff, bool aff_is_tiled, const float* m_in, float* m_out, void* scratch,
+                     size_t scratch_bytes, int B, int C, int H, int W, const Dilations& dil, int iters,
+                     unsigned* cls_max, int dev, cudaStream_t s);
 int launch_clean(const float* m, const float* labels, float* cleaned, unsigned* cls_max, int B, int C, int h, int w,
                  int H, int W, cudaStream_t s);
 int launch_pseudo_labels(const float* m, const float* labels, const unsigned* cls_max, uint8_t* label,

@@ -1,18 +1,22 @@
-// Propagation kernels: replace the loop at reference models/mods/pamr.py:138-140
+// Propagation: replaces the loop at reference models/mods/pamr.py:138-140
 //   for _ in range(num_iter):  m = aff_m(mask);  mask = (m * x).sum(2)
 // i.e. M'[b,c,y,x] = sum_p w[b,p,y,x] * M[b,c,clamp(y+dy_p),clamp(x+dx_p)].
 // The reference materialises the [B,C,48,H,W] unfolded tensor every iteration; here every
 // iteration is one stencil pass (read affinity once, mask once, write mask once).
 //
-// This file holds the GENERIC kernel (any dilation list, any C, any H/W): one thread per pixel,
-// neighbours fetched through L1 with clamped coordinates.  The tuned sm_100a kernel for the
-// standard dilation set lives in pamr_propagate_sm100.cu and is selected in launch_propagate().
+// This file holds the iteration driver, the GENERIC kernel (any dilation list, any C, any H/W:
+// one thread per pixel, neighbours fetched through L1 with clamped coordinates) and the STRIP
+// kernel that covers the few right-most columns the tuned kernel leaves out.  The tuned sm_100a
+// kernel for the standard dilation set lives in pamr_propagate_sm100.cu.
 #include "pamr_common.cuh"
 
 namespace pamr {
 
-int launch_propagate_tuned(const float* aff, const float* m_in, float* m_out, int B, int C, int H, int W,
-                           const Dilations& dil, unsigned* cls_max, int dev, cudaStream_t s, bool* handled);
+// pamr_propagate_sm100.cu
+int tuned_width(int W);
+int launch_repack(const float* src, float* dst, int planes, int H, int W, int Wp, cudaStream_t s);
+int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, int src_pitch, float* dst,
+                           int dst_pitch, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s);
 
 namespace {
 
@@ -20,15 +24,17 @@ constexpr int GEN_BX = 32;
 constexpr int GEN_BY = 8;
 constexpr int GEN_CC = 7;  // classes accumulated per pass over the taps
 
+// src / dst rows may be pitched; aff is the standard [B,P,H,W] layout.
 __global__ void __launch_bounds__(GEN_BX * GEN_BY)
-propagate_generic_kernel(const float* __restrict__ aff, const float* __restrict__ m_in, float* __restrict__ m_out,
-                         int C, int H, int W, Dilations dil, unsigned* __restrict__ cls_max) {
+propagate_generic_kernel(const float* __restrict__ aff, const float* __restrict__ m_in, int src_pitch,
+                         float* __restrict__ m_out, int dst_pitch, int C, int H, int W, Dilations dil,
+                         unsigned* __restrict__ cls_max) {
     const int x = blockIdx.x * GEN_BX + threadIdx.x;
     const int y = blockIdx.y * GEN_BY + threadIdx.y;
     const int b = blockIdx.z;
     const bool valid = (x < W) && (y < H);
     const int xc = min(x, W - 1), yc = min(y, H - 1);
-    const size_t HW = (size_t)H * W;
+    const size_t HW = (size_t)H * W, HPs = (size_t)H * src_pitch, HPd = (size_t)H * dst_pitch;
     const int P = 8 * dil.nd;
     const float* __restrict__ wp = aff + (size_t)b * P * HW + (size_t)yc * W + xc;
 
@@ -36,7 +42,7 @@ propagate_generic_kernel(const float* __restrict__ aff, const float* __restrict_
         float acc[GEN_CC];
 #pragma unroll
         for (int cc = 0; cc < GEN_CC; ++cc) acc[cc] = 0.f;
-        const float* __restrict__ mb = m_in + ((size_t)b * C + c0) * HW;
+        const float* __restrict__ mb = m_in + ((size_t)b * C + c0) * HPs;
         for (int i = 0; i < dil.nd; ++i) {
             const int d = dil.d[i];
 #pragma unroll
@@ -44,16 +50,16 @@ propagate_generic_kernel(const float* __restrict__ aff, const float* __restrict_
                 const int yy = clampi(yc + tap_dy(j) * d, 0, H - 1);
                 const int xx = clampi(xc + tap_dx(j) * d, 0, W - 1);
                 const float wv = __ldg(wp + (size_t)(8 * i + j) * HW);
-                const float* __restrict__ q = mb + (size_t)yy * W + xx;
+                const float* __restrict__ q = mb + (size_t)yy * src_pitch + xx;
 #pragma unroll
                 for (int cc = 0; cc < GEN_CC; ++cc)
-                    if (c0 + cc < C) acc[cc] = fmaf(wv, __ldg(q + (size_t)cc * HW), acc[cc]);
+                    if (c0 + cc < C) acc[cc] = fmaf(wv, __ldg(q + (size_t)cc * HPs), acc[cc]);
             }
         }
 #pragma unroll
         for (int cc = 0; cc < GEN_CC; ++cc) {
             if (c0 + cc < C) {
-                if (valid) m_out[((size_t)b * C + c0 + cc) * HW + (size_t)y * W + x] = acc[cc];
+                if (valid) m_out[((size_t)b * C + c0 + cc) * HPd + (size_t)y * dst_pitch + x] = acc[cc];
                 if (cls_max != nullptr) {
                     unsigned u = valid ? ordered_from_float(acc[cc]) : 0u;
                     u = __reduce_max_sync(0xffffffffu, u);
@@ -64,8 +70,42 @@ propagate_generic_kernel(const float* __restrict__ aff, const float* __restrict_
     }
 }
 
+// Remainder strip x in [x_begin, W) next to the tuned kernel's tiles (standard dilations, tiled
+// affinity).  One thread per (pixel, class): the strip is a few thousand pixels, so parallelism
+// over classes is what keeps this launch in the microsecond range.
+__global__ void __launch_bounds__(256)
+propagate_strip_kernel(const float* __restrict__ aff, AffTiling tiling, const float* __restrict__ m_in, int src_pitch,
+                       float* __restrict__ m_out, int dst_pitch, int B, int C, int H, int W, int x_begin,
+                       unsigned* __restrict__ cls_max) {
+    const int xw = W - x_begin;
+    const long long total = (long long)B * C * H * xw;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int x = x_begin + (int)(t % xw);
+    const int y = (int)((t / xw) % H);
+    const int c = (int)((t / ((long long)xw * H)) % C);
+    const int b = (int)(t / ((long long)xw * H * C));
+    const float* __restrict__ pl = m_in + ((size_t)b * C + c) * H * src_pitch;
+    const float* __restrict__ wp = aff + aff_tiled_index(tiling, b, 0, y, x);
+    const size_t sstride = (size_t)tiling.R * 32;
+    const int dils[6] = {1, 2, 4, 8, 12, 24};
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int d = dils[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int yy = clampi(y + tap_dy(j) * d, 0, H - 1);
+            const int xx = clampi(x + tap_dx(j) * d, 0, W - 1);
+            acc = fmaf(__ldg(wp + tap_seq(8 * i + j) * sstride), __ldg(pl + (size_t)yy * src_pitch + xx), acc);
+        }
+    }
+    m_out[(((size_t)b * C + c) * H + y) * dst_pitch + x] = acc;
+    if (cls_max != nullptr) atomicMax(cls_max + (size_t)b * C + c, ordered_from_float(acc));
+}
+
 __global__ void class_max_kernel(const float* __restrict__ m, unsigned* __restrict__ cls_max, size_t HW) {
-    // one block per (b,c) plane slice; used only when iters == 0 and a max is requested
+    // used only when iters == 0 and a max is requested
     const size_t plane = blockIdx.y;
     const float* __restrict__ p = m + plane * HW;
     unsigned u = 0u;
@@ -75,10 +115,57 @@ __global__ void class_max_kernel(const float* __restrict__ m, unsigned* __restri
     if ((threadIdx.x & 31) == 0 && u != 0u) atomicMax(cls_max + plane, u);
 }
 
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int launch_generic(const float* aff, const float* src, int src_pitch, float* dst, int dst_pitch, int B, int C, int H,
+                   int W, const Dilations& dil, unsigned* cls_max, cudaStream_t s) {
+    dim3 block(GEN_BX, GEN_BY);
+    dim3 grid((W + GEN_BX - 1) / GEN_BX, (H + GEN_BY - 1) / GEN_BY, B);
+    if (grid.y > 65535 || grid.z > 65535)
+        return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: H/8 and B must be <= 65535");
+    propagate_generic_kernel<<<grid, block, 0, s>>>(aff, src, src_pitch, dst, dst_pitch, C, H, W, dil, cls_max);
+    count_launch();
+    PAMR_CUDA_TRY(cudaGetLastError());
+    return PAMR_OK;
+}
+
+int launch_strip(const float* aff_tiled, const AffTiling& tiling, const float* src, int src_pitch, float* dst,
+                 int dst_pitch, int B, int C, int H, int W, int x_begin, unsigned* cls_max, cudaStream_t s) {
+    const long long total = (long long)B * C * H * (W - x_begin);
+    const long long blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffLL) return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: strip too large");
+    propagate_strip_kernel<<<(unsigned)blocks, 256, 0, s>>>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W,
+                                                           x_begin, cls_max);
+    count_launch();
+    PAMR_CUDA_TRY(cudaGetLastError());
+    return PAMR_OK;
+}
+
+struct ScratchPlan {
+    size_t pingpong_each, aff_tiled, total;
+};
+ScratchPlan plan_scratch(int B, int C, int H, int W, const Dilations& dil, int iters, bool aff_is_tiled) {
+    ScratchPlan p{0, 0, 0};
+    if (iters <= 0) return p;
+    // two ping-pong buffers with rows pitched to a multiple of 4 floats (TMA needs 16-byte global
+    // strides; W = 321 is not)
+    const size_t Wp = align_up((size_t)W, 4);
+    p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * H * Wp, 256);
+    const AffTiling t = tuned_tiling(H, W, dil);
+    if (t.R > 0 && !aff_is_tiled) p.aff_tiled = align_up(sizeof(float) * aff_tiled_floats(B, t), 256);
+    p.total = 2 * p.pingpong_each + p.aff_tiled;
+    return p;
+}
+
 }  // namespace
 
-int launch_propagate(const float* aff, const float* m_in, float* m_out, float* m_tmp, int B, int C, int H, int W,
-                     const Dilations& dil, int iters, unsigned* cls_max, int dev, cudaStream_t s) {
+size_t propagate_scratch_bytes(int B, int C, int H, int W, const Dilations& dil, int iters, bool aff_is_tiled) {
+    return plan_scratch(B, C, H, W, dil, iters, aff_is_tiled).total;
+}
+
+int launch_propagate(const float* aff, bool aff_is_tiled, const float* m_in, float* m_out, void* scratch,
+                     size_t scratch_bytes, int B, int C, int H, int W, const Dilations& dil, int iters,
+                     unsigned* cls_max, int dev, cudaStream_t s) {
     const size_t N = (size_t)B * C * H * W;
     if (cls_max != nullptr) PAMR_CUDA_TRY(cudaMemsetAsync(cls_max, 0, sizeof(unsigned) * (size_t)B * C, s));
     if (iters <= 0) {
@@ -91,27 +178,53 @@ int launch_propagate(const float* aff, const float* m_in, float* m_out, float* m
         }
         return PAMR_OK;
     }
-    if (iters > 1 && m_tmp == nullptr)
-        return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: m_tmp is required when iters > 1");
+    const ScratchPlan plan = plan_scratch(B, C, H, W, dil, iters, aff_is_tiled);
+    if (scratch == nullptr || scratch_bytes < plan.total)
+        return set_error(PAMR_ERR_WORKSPACE, "propagate: scratch of %zu bytes given, %zu needed", scratch_bytes,
+                         plan.total);
+    if (((uintptr_t)scratch & 255) != 0)
+        return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: scratch must be 256-byte aligned");
+    const int Wp = (int)align_up((size_t)W, 4);
+    float* P[2] = {(float*)scratch, (float*)((char*)scratch + plan.pingpong_each)};
+    const AffTiling tiling = tuned_tiling(H, W, dil);
+    const bool tuned = tiling.R > 0;
+    if (!tuned && aff_is_tiled)
+        return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: tiled affinity without the tuned kernel");
+    if (tuned && !aff_is_tiled) {
+        float* at = (float*)((char*)scratch + 2 * plan.pingpong_each);
+        int rc = launch_aff_relayout(aff, at, B, H, W, tiling, s);
+        if (rc != PAMR_OK) return rc;
+        aff = at;
+    }
+    const int Wt = tuned ? tuned_width(W) : 0;
 
     const float* src = m_in;
-    for (int it = 0; it < iters; ++it) {
-        // ping-pong so that the last iteration lands in m_out and m_in is never written
-        float* dst = ((iters - 1 - it) & 1) ? m_tmp : m_out;
-        unsigned* mx = (it == iters - 1) ? cls_max : nullptr;
-        bool handled = false;
-        int rc = launch_propagate_tuned(aff, src, dst, B, C, H, W, dil, mx, dev, s, &handled);
+    int src_pitch = W;
+    int next = 0;  // next free ping-pong buffer
+    if (tuned && ((W & 3) != 0 || ((uintptr_t)m_in & 15) != 0)) {
+        int rc = launch_repack(m_in, P[0], B * C, H, W, Wp, s);
         if (rc != PAMR_OK) return rc;
-        if (!handled) {
-            dim3 block(GEN_BX, GEN_BY);
-            dim3 grid((W + GEN_BX - 1) / GEN_BX, (H + GEN_BY - 1) / GEN_BY, B);
-            if (grid.y > 65535 || grid.z > 65535)
-                return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: H/8 and B must be <= 65535");
-            propagate_generic_kernel<<<grid, block, 0, s>>>(aff, src, dst, C, H, W, dil, mx);
-            count_launch();
-            PAMR_CUDA_TRY(cudaGetLastError());
+        src = P[0];
+        src_pitch = Wp;
+        next = 1;
+    }
+    for (int it = 0; it < iters; ++it) {
+        const bool last = (it == iters - 1);
+        float* dst = last ? m_out : P[next];
+        const int dst_pitch = last ? W : Wp;
+        unsigned* mx = last ? cls_max : nullptr;
+        int rc;
+        if (tuned) {
+            rc = launch_propagate_tuned(aff, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, mx, dev, s);
+            if (rc == PAMR_OK && Wt < W)
+                rc = launch_strip(aff, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, mx, s);
+        } else {
+            rc = launch_generic(aff, src, src_pitch, dst, dst_pitch, B, C, H, W, dil, mx, s);
         }
+        if (rc != PAMR_OK) return rc;
         src = dst;
+        src_pitch = dst_pitch;
+        next ^= 1;
     }
     return PAMR_OK;
 }

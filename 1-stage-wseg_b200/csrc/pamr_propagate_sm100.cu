@@ -1,13 +1,730 @@
-// Tuned sm_100a propagation kernel for the standard dilation set (placeholder: not selected yet).
+// Tuned sm_100a propagation kernel for the standard dilation set [1,2,4,8,12,24]
+// (reference models/mods/pamr.py:138-140 with core/config.py:92).
+//
+//   M'[b,c,y,x] = sum_{p<48} w[b,p,y,x] * M[b,c,clamp(y+dy_p),clamp(x+dx_p)]
+//
+// Design (DESIGN.md "propagate_sm100"):
+//  * persistent CTAs, one per SM; a CTA owns a 32 x (4*R) pixel tile (R = 8, 9 or 10 rows per thread);
+//  * 4 compute warps: lane = x, each thread owns a vertical strip of R pixels, so that one
+//    shared-memory load feeds up to 3*R/(R+2d) taps (register reuse along y): ~32 LDS per
+//    pixel-class instead of 48;
+//  * the tile's 48 affinity weights per pixel (48*R words per thread) are read from HBM ONCE per
+//    tile and parked in Tensor Memory (tcgen05.st), 1 TMEM lane per thread; every class group
+//    re-reads them with tcgen05.ld -- a data path that does not compete with LDS -- instead of
+//    holding them in registers or re-reading them through L1;
+//  * a producer warp streams the 21 class planes of the tile (+24 px halo, 80 x (4R+48) floats)
+//    through an 8-slot shared-memory ring with TMA (cp.async.bulk.tensor.3d) + mbarriers; TMA
+//    zero-fills outside the image, so for border tiles the producer warp patches the halo in
+//    shared memory to replicate padding (pamr.py:50) before releasing the slot;
+//  * compute warps take 3 class planes at a time (27-30 accumulators), FP32 FMA, and store the
+//    result with coalesced 128-byte rows; the per-(b,c) max for pseudo_gtmask is fused into the
+//    last iteration (warp reduce + atomicMax).
+#include <cuda.h>
+
+#include <atomic>
+#include <cstdlib>
+#include <mutex>
+
 #include "pamr_common.cuh"
 
 namespace pamr {
 
-int launch_propagate_tuned(const float* aff, const float* m_in, float* m_out, int B, int C, int H, int W,
-                           const Dilations& dil, unsigned* cls_max, int dev, cudaStream_t s, bool* handled) {
-    (void)aff; (void)m_in; (void)m_out; (void)B; (void)C; (void)H; (void)W; (void)dil; (void)cls_max; (void)dev; (void)s;
-    *handled = false;
+namespace {
+
+constexpr int TX = 32;
+constexpr int HALO = 24;
+constexpr int WIN_W = TX + 2 * HALO;  // 80 floats = 320 B rows in shared memory
+constexpr int NW = 4;                 // warps per compute group (= TMEM lane quarters)
+constexpr int NG = 3;                 // compute groups that share the tile's weights in TMEM (class c -> group c % NG)
+constexpr int NWC = NG * NW;          // compute warps
+constexpr int NSLOT = 8;              // class-plane slots in the shared-memory ring
+#ifndef PAMR_CC
+#define PAMR_CC 1
+#endif
+constexpr int CC = PAMR_CC;           // class planes per compute pass
+constexpr int NTHREADS = (NWC + 1) * 32;
+constexpr int WB = 16;                // weights per tcgen05.ld batch
+
+__host__ __device__ constexpr int dil_of(int id) { return id == 0 ? 1 : id == 1 ? 2 : id == 2 ? 4 : id == 3 ? 8 : id == 4 ? 12 : 24; }
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// non-blocking poll (try_wait may suspend the thread for a while before answering)
+__device__ __forceinline__ bool mbar_poll(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_test(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]), "f"(r[8]),
+        "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+#ifdef PAMR_BODY_NO_TMEM
+    for (int j = 0; j < 16; ++j) r[j] = __uint_as_float(taddr + j) * 1e-30f;
+    return;
+#endif
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
+          "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+        : "r"(taddr));
+}
+// tcgen05.wait::ld, with the batch's registers tied through the asm so that no consumer of the
+// loaded values can be scheduled above the wait.
+__device__ __forceinline__ void tmem_wait_ld(float (&r)[16]) {
+#ifdef PAMR_BODY_NO_TMEM
+    return;
+#endif
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+                   "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]));
+}
+
+// ---------------------------------------------------------------- shared-memory layout
+template <int R>
+struct Cfg {
+    static constexpr int TY = NW * R;
+    static constexpr int WIN_H = TY + 2 * HALO;
+    static constexpr int SLOT_FLOATS = WIN_W * WIN_H;
+    static constexpr int SLOT_BYTES = SLOT_FLOATS * 4;
+    static constexpr size_t SMEM_BYTES = (size_t)NSLOT * SLOT_BYTES + 1024;
+};
+
+struct Ctrl {  // lives in the last 1 KB of dynamic shared memory
+    unsigned long long tma_bar[NSLOT];
+    unsigned long long ready_bar[NSLOT];
+    unsigned long long empty_bar[NSLOT];
+    uint32_t tmem_base;
+};
+
+struct Params {
+    const float* aff;  // tile-major affinity (pamr_common.cuh), tiles_x_aff tile columns
+    float* dst;        // [B,C,H,dst_pitch]
+    unsigned* cls_max; // [B,C] or nullptr
+    int stagger_cta_ns, stagger_grp_ns;  // experiment knobs (env PAMR_B200_STAGGER_CTA / _GRP)
+    long long* dbg;    // nullptr, or timeline buffer (debug hook pamr_debug_set_timeline): 2 x 4096 x {clock, code}
+    int dst_pitch;
+    int B, C, H, W;
+    int tiles_x, tiles_y, ntiles;  // tiles of this launch (tiles_x may exclude the remainder strip)
+    int tiles_x_aff;               // tile columns of the affinity layout
+};
+
+// ---------------------------------------------------------------- TMEM weight layout
+// Per thread (= TMEM lane) the 48*R weights of its R pixels are laid out in consumption order:
+//   columns [0, 12R)            centre column (b = 0): tap sequence s = 2*id + (a>0), R rows each
+//   columns SIDE0 + 32*g ...    side group g = 6*bi + id (bi = 0: b = -1, bi = 1: b = +1):
+//                               (a+1)*R + i for a = -1,0,+1  (3R <= 30 of the 32 columns used)
+// so that every side group is one aligned tcgen05.ld.x32 and the b = -1 / b = +1 halves can share
+// one (rolled) copy of the code: the unrolled loop body must stay inside the 32 KB instruction cache.
+template <int R>
+struct TmemLayout {
+    static constexpr int CPAD = (12 * R + WB - 1) / WB * WB;  // centre columns padded to a batch
+    static constexpr int SIDE0 = CPAD;
+    static constexpr int NCOLS = CPAD + 12 * 32;              // <= 512
+    static_assert(NCOLS <= 512, "TMEM columns");
+};
+
+template <int R>
+__host__ __device__ constexpr int seq_col(int s) {
+    return (s < 12) ? s * R : TmemLayout<R>::SIDE0 + ((s - 12) / 3) * 32 + ((s - 12) % 3) * R;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
+#ifdef PAMR_BODY_NO_TMEM
+    for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(taddr + j) * 1e-30f;
+    return;
+#endif
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
+          "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]),
+          "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]),
+          "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld32(float (&r)[32]) {
+#ifdef PAMR_BODY_NO_TMEM
+    return;
+#endif
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+                   "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]),
+                   "+f"(r[16]), "+f"(r[17]), "+f"(r[18]), "+f"(r[19]), "+f"(r[20]), "+f"(r[21]), "+f"(r[22]),
+                   "+f"(r[23]), "+f"(r[24]), "+f"(r[25]), "+f"(r[26]), "+f"(r[27]), "+f"(r[28]), "+f"(r[29]),
+                   "+f"(r[30]), "+f"(r[31]));
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, float r0) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "f"(r0));
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, float r0, float r1) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "f"(r0), "f"(r1));
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "f"(r[0]),
+                 "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]));
+}
+
+// ---------------------------------------------------------------- compute body
+// One pass over the 48 taps for N (<= CC) class planes resident in the ring.
+// sp[n] points at this thread's pixel (row R*warp, column lane) of plane n inside its slot,
+// i.e. slot + (R*warp + HALO)*WIN_W + lane + HALO; neighbours are immediate offsets.
+// Two FMAs on adjacent rows as one packed FFMA2 (fma.rn.f32x2).  A scalar FFMA whose three source
+// registers are all distinct issues only every ~1.8 cycles per SM sub-partition (measured,
+// tools/ubench3.cu); the packed form retires two FMAs per ~2.4 cycles.  The mov.b64 packs are
+// free when ptxas allocates the operands as aligned register pairs (TMEM batches, the row strip
+// and the accumulators all are, for even R and even row shifts).
+__device__ __forceinline__ void fma2(float& a0, float& a1, float w0, float w1, float v0, float v1) {
+    unsigned long long A, W2, V2;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(W2) : "f"(w0), "f"(w1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(V2) : "f"(v0), "f"(v1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(A) : "l"(W2), "l"(V2));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(A));
+}
+
+template <int R, int N>
+__device__ __forceinline__ void compute_pass(const float* (&sp)[CC], uint32_t tbase, float (&acc)[CC][R]) {
+    using L = TmemLayout<R>;
+#ifdef PAMR_NO_FFMA2
+    constexpr bool kPacked = false;
+#else
+    constexpr bool kPacked = (R % 2 == 0);
+#endif
+    constexpr int NCB = L::CPAD / WB;  // centre batches
+    float wc[2][WB];
+    float ws[2][32];
+    tmem_ld16(tbase, wc[0]);
+
+    // ---- centre column (b = 0): rows y+-d for all dilations, merged into one register strip
+    {
+        float v[CC][R + 2 * HALO];
+#pragma unroll
+        for (int r = -HALO; r < R + HALO; ++r) {
+            bool need = false;
+#pragma unroll
+            for (int id = 0; id < 6; ++id) {
+                const int d = dil_of(id);
+                need = need || (r >= -d && r < R - d) || (r >= d && r < R + d);
+            }
+            if (need) {
+#pragma unroll
+                for (int n = 0; n < N; ++n) v[n][r + HALO] = sp[n][r * WIN_W];
+            }
+        }
+        int q = 0;  // compile-time after full unrolling
+#pragma unroll
+        for (int id = 0; id < 6; ++id) {
+            const int d = dil_of(id);
+#pragma unroll
+            for (int a = -1; a <= 1; a += 2) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const bool pair = kPacked && (d % 2 == 0);  // rows (i, i+1) as one FFMA2
+                    if (pair && (i % 2 == 1)) continue;          // odd row handled with its even partner
+                    if (q % WB == 0) {  // batch boundary: wait for this batch, prefetch the next one
+                        tmem_wait_ld(wc[(q / WB) & 1]);
+                        if (q / WB + 1 < NCB) tmem_ld16(tbase + (q / WB + 1) * WB, wc[(q / WB + 1) & 1]);
+                        else tmem_ld32(tbase + L::SIDE0, ws[0]);  // first side group
+                    }
+                    if (pair) {
+#pragma unroll
+                        for (int n = 0; n < N; ++n)
+                            fma2(acc[n][i], acc[n][i + 1], wc[(q / WB) & 1][q % WB], wc[(q / WB) & 1][q % WB + 1],
+                                 v[n][i + a * d + HALO], v[n][i + 1 + a * d + HALO]);
+                        q += 2;
+                    } else {
+                        const float w = wc[(q / WB) & 1][q % WB];
+#pragma unroll
+                        for (int n = 0; n < N; ++n) acc[n][i] = fmaf(w, v[n][i + a * d + HALO], acc[n][i]);
+                        ++q;
+                    }
+                }
+            }
+        }
+    }
+    // ---- side columns: bi = 0 (b = -1), bi = 1 (b = +1); rolled so that both share one code copy
+#pragma unroll 1
+    for (int bi = 0; bi < 2; ++bi) {
+        const int sgn = bi * 2 - 1;
+#pragma unroll
+        for (int id = 0; id < 6; ++id) {
+            const int d = dil_of(id);
+            float (&w)[32] = ws[id & 1];
+            tmem_wait_ld32(w);
+            // prefetch the next side group (the last one of b = +1 has no successor)
+            if (id < 5) tmem_ld32(tbase + L::SIDE0 + (bi * 6 + id + 1) * 32, ws[(id + 1) & 1]);
+            else if (bi == 0) tmem_ld32(tbase + L::SIDE0 + 6 * 32, ws[0]);
+            float v[CC][R + 2 * HALO];
+            const int coff = sgn * d;
+#pragma unroll
+            for (int r = -d; r < R + d; ++r) {
+                const bool need = (r < R - d) || (r >= 0 && r < R) || (r >= d);
+                if (need) {
+#pragma unroll
+                    for (int n = 0; n < N; ++n) v[n][r + HALO] = sp[n][r * WIN_W + coff];
+                }
+            }
+#pragma unroll
+            for (int a = -1; a <= 1; ++a) {
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    const bool pair = kPacked && ((a * d) % 2 == 0);  // rows (i, i+1) as one FFMA2
+                    if (pair && (i % 2 == 1)) continue;
+                    if (pair) {
+#pragma unroll
+                        for (int n = 0; n < N; ++n)
+                            fma2(acc[n][i], acc[n][i + 1], w[(a + 1) * R + i], w[(a + 1) * R + i + 1], v[n][i + a * d + HALO],
+                                 v[n][i + 1 + a * d + HALO]);
+                    } else {
+                        const float wv = w[(a + 1) * R + i];
+#pragma unroll
+                        for (int n = 0; n < N; ++n) acc[n][i] = fmaf(wv, v[n][i + a * d + HALO], acc[n][i]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ bool needs_patch(int x0, int y0, int H, int W) {
+    return x0 < HALO || y0 < HALO || x0 + TX + HALO > W || y0 + Cfg<R>::TY + HALO > H;
+}
+
+// Border tiles: TMA zero-filled everything outside the image; overwrite it with the clamped
+// (replicate-padded) value.  Window element (wy,wx) <-> image pixel (y0-24+wy, x0-24+wx).
+template <int R>
+__device__ __forceinline__ void patch_window(float* slot, int x0, int y0, int H, int W, int lane) {
+    constexpr int WIN_H = Cfg<R>::WIN_H;
+    const int vx0 = max(0, HALO - x0), vx1 = min(WIN_W, W - x0 + HALO);
+    const int vy0 = max(0, HALO - y0), vy1 = min(WIN_H, H - y0 + HALO);
+    if (vx0 == 0 && vx1 == WIN_W && vy0 == 0 && vy1 == WIN_H) return;
+    // left / right columns of the valid rows: one broadcast read + one store per row and side
+    if (vx0 > 0) {
+#pragma unroll 4
+        for (int wy = vy0; wy < vy1; ++wy) {
+            const float v = slot[wy * WIN_W + vx0];
+            if (lane < vx0) slot[wy * WIN_W + lane] = v;
+        }
+    }
+    if (vx1 < WIN_W) {
+#pragma unroll 4
+        for (int wy = vy0; wy < vy1; ++wy) {
+            const float v = slot[wy * WIN_W + vx1 - 1];
+            if (vx1 + lane < WIN_W) slot[wy * WIN_W + vx1 + lane] = v;
+            if (vx1 + 32 + lane < WIN_W) slot[wy * WIN_W + vx1 + 32 + lane] = v;
+        }
+    }
+    if (vy0 == 0 && vy1 == WIN_H) return;
+    __syncwarp();
+    // rows above / below: replicate the (already side-patched) first / last valid row
+#pragma unroll
+    for (int k = 0; k < (WIN_W + 31) / 32; ++k) {
+        const int wx = 32 * k + lane;
+        if (wx < WIN_W) {
+            if (vy0 > 0) {
+                const float v = slot[vy0 * WIN_W + wx];
+                for (int wy = 0; wy < vy0; ++wy) slot[wy * WIN_W + wx] = v;
+            }
+            if (vy1 < WIN_H) {
+                const float v = slot[(vy1 - 1) * WIN_W + wx];
+                for (int wy = vy1; wy < WIN_H; ++wy) slot[wy * WIN_W + wx] = v;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void compute_bar_sync() {  // the NWC compute warps only (named barrier 1)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(NWC * 32) : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(NTHREADS, 1)
+propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params prm) {
+    using C_ = Cfg<R>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float* slots = reinterpret_cast<float*>(smem_raw);
+    Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem_raw + (size_t)NSLOT * C_::SLOT_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int C = prm.C, H = prm.H, W = prm.W;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSLOT; ++s) {
+            mbar_init(smem_u32(&ctrl->tma_bar[s]), 1);
+            mbar_init(smem_u32(&ctrl->ready_bar[s]), 1);
+            mbar_init(smem_u32(&ctrl->empty_bar[s]), NW);  // the NW warps of the group that read the slot
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctrl->tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const int my_tiles = (prm.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tiles_per_img = prm.tiles_x * prm.tiles_y;
+
+    if (warp == NWC) {
+        // ===================== producer warp: TMA issue + border patch =====================
+        // Sequence number n = (tile_iter, class) -> slot n % NSLOT.  A consumer waits for tma_bar
+        // (bytes landed) and ready_bar (halo patched).  For interior tiles ready_bar is signalled
+        // right at issue time, so the producer is not on the consumers' critical path.
+        const long long total = (long long)my_tiles * C;
+        long long n_issue = 0, n_done = 0;
+        while (n_done < total) {
+            int did = 0, x0 = 0, y0 = 0;
+            if (n_issue < total) {
+                const int s = (int)(n_issue % NSLOT);
+                const uint32_t round = (uint32_t)(n_issue / NSLOT);
+                const int ti = (int)(n_issue / C), c = (int)(n_issue % C);
+                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                const int b = tile / tiles_per_img, t = tile % tiles_per_img;
+                x0 = (t % prm.tiles_x) * TX, y0 = (t / prm.tiles_x) * C_::TY;
+                const bool border = needs_patch<R>(x0, y0, H, W);
+                if (lane == 0 && mbar_poll(smem_u32(&ctrl->empty_bar[s]), (round & 1u) ^ 1u)) {
+                    const uint32_t bar = smem_u32(&ctrl->tma_bar[s]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive_expect_tx(bar, C_::SLOT_BYTES);
+                    tma_load_3d(smem_u32(slots + (size_t)s * C_::SLOT_FLOATS), &tmap, bar, x0 - HALO, y0 - HALO, b * C + c);
+                    if (!border) mbar_arrive(smem_u32(&ctrl->ready_bar[s]));
+                    did = 1;
+                }
+                did = __shfl_sync(0xffffffffu, did, 0);
+                if (did) {
+                    ++n_issue;
+                }
+            }
+            // skip over interior-tile entries (nothing to patch, ready already signalled)
+            while (n_done < n_issue) {
+                const int ti = (int)(n_done / C);
+                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                const int t = tile % tiles_per_img;
+                const int px0 = (t % prm.tiles_x) * TX, py0 = (t / prm.tiles_x) * C_::TY;
+                if (needs_patch<R>(px0, py0, H, W)) break;
+                ++n_done;
+            }
+            if (n_done < n_issue) {
+                const int s = (int)(n_done % NSLOT);
+                const uint32_t round = (uint32_t)(n_done / NSLOT);
+                int landed = (lane == 0) ? (int)mbar_poll(smem_u32(&ctrl->tma_bar[s]), round & 1u) : 0;
+                landed = __shfl_sync(0xffffffffu, landed, 0);
+                if (landed) {
+                    const int ti = (int)(n_done / C);
+                    const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                    const int t = tile % tiles_per_img;
+                    patch_window<R>(slots + (size_t)s * C_::SLOT_FLOATS, (t % prm.tiles_x) * TX, (t / prm.tiles_x) * C_::TY,
+                                    H, W, lane);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&ctrl->ready_bar[s]));
+                    ++n_done;
+                    did = 1;
+                }
+            }
+            if (!did) __nanosleep(32);  // do not steal issue slots from the compute warp on this SMSP
+        }
+    } else {
+        // ===================== compute warps: 2 groups x NW warps =====================
+        const int grp = warp / NW, wq = warp % NW;  // wq = TMEM lane quarter; both groups share the weights
+        const uint32_t tbase = ctrl->tmem_base + ((uint32_t)(wq * 32) << 16);
+        int dn = 0;  // timeline events written by this group's leader lane of CTA 0
+        if ((blockIdx.x & 1) && prm.stagger_cta_ns > 0) __nanosleep(prm.stagger_cta_ns);
+#define PAMR_EV(code)                                                                         \
+    do {                                                                                      \
+        if (prm.dbg != nullptr && blockIdx.x == 0 && grp < 2 && wq == 0 && lane == 0 && dn < 4096) {      \
+            prm.dbg[((grp & 1) * 4096 + dn) * 2] = clock64();                                        \
+            prm.dbg[((grp & 1) * 4096 + dn) * 2 + 1] = (code);                                       \
+            ++dn;                                                                             \
+        }                                                                                     \
+    } while (0)
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int b = tile / tiles_per_img, t = tile % tiles_per_img;
+            const int x0 = (t % prm.tiles_x) * TX, y0 = (t / prm.tiles_x) * C_::TY;
+            const int x = x0 + lane, yw = y0 + wq * R;
+            const bool xok = x < W;
+            const long long seq0 = (long long)ti * C;
+
+            // ---- park the tile's 48*R weights per thread in TMEM (layout: TmemLayout); each group
+            //      loads half of the taps for the lanes it shares with its sibling warp
+            PAMR_EV(1);
+            if (ti > 0) compute_bar_sync();  // nobody still reads the previous tile's weights
+            PAMR_EV(2);
+            {
+                // tile-major layout: this thread's weights are ap[(s*R + i)*32], s = tap sequence index
+                const int ty = t / prm.tiles_x, tx = t % prm.tiles_x;
+                const float* __restrict__ ap =
+                    prm.aff + (((((size_t)b * prm.tiles_y + ty) * prm.tiles_x_aff + tx) * 4 + wq) * 48 * R) * 32 + lane;
+                // FILL_TAPS*R loads are in flight before the first TMEM store: memory-level
+                // parallelism is what bounds this phase (the accumulators are not live here)
+                constexpr int TAPS_PER_GROUP = 48 / NG, FILL_TAPS = 8;
+#pragma unroll
+                for (int h = 0; h < TAPS_PER_GROUP / FILL_TAPS; ++h) {
+                    const int s0 = TAPS_PER_GROUP * grp + h * FILL_TAPS;  // grp is warp-uniform; offsets below are immediates
+                    const float* __restrict__ bp = ap + (size_t)s0 * R * 32;
+                    float r[FILL_TAPS][R];
+#pragma unroll
+                    for (int k = 0; k < FILL_TAPS; ++k)
+#pragma unroll
+                        for (int i = 0; i < R; ++i) r[k][i] = __ldg(bp + (k * R + i) * 32);
+#pragma unroll
+                    for (int k = 0; k < FILL_TAPS; ++k) {
+                        const uint32_t col = tbase + seq_col<R>(s0 + k);
+                        tmem_st8(col, r[k]);
+                        if (R == 9) tmem_st1(col + 8, r[k][R - 1]);
+                        if (R == 10) tmem_st2(col + 8, r[k][R - 2], r[k][R - 1]);
+                    }
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+            PAMR_EV(3);
+            compute_bar_sync();  // both halves of the weights are visible to both groups
+            PAMR_EV(4);
+            if (grp != 0 && prm.stagger_grp_ns > 0) __nanosleep(prm.stagger_grp_ns * grp);
+
+            for (int k = grp; k < C; k += NG) {
+                const int c0 = k, n = 1;
+                const float* sp[CC];
+                PAMR_EV(100 + k);
+#pragma unroll
+                for (int j = 0; j < CC; ++j) {
+                    const long long sq = seq0 + c0 + (j < n ? j : 0);
+                    const int s = (int)(sq % NSLOT);
+                    if (j < n) {
+                        mbar_wait(smem_u32(&ctrl->tma_bar[s]), (uint32_t)(sq / NSLOT) & 1u);
+                        mbar_wait(smem_u32(&ctrl->ready_bar[s]), (uint32_t)(sq / NSLOT) & 1u);
+                    }
+                    sp[j] = slots + (size_t)s * C_::SLOT_FLOATS + (wq * R + HALO) * WIN_W + lane + HALO;
+                }
+                PAMR_EV(6);
+                float acc[CC][R];
+#pragma unroll
+                for (int j = 0; j < CC; ++j)
+#pragma unroll
+                    for (int i = 0; i < R; ++i) acc[j][i] = 0.f;
+                compute_pass<R, 1>(sp, tbase, acc);
+                // release the slots as early as possible
+                __syncwarp();
+                PAMR_EV(7);
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < CC; ++j)
+                        if (j < n) mbar_arrive(smem_u32(&ctrl->empty_bar[(int)((seq0 + c0 + j) % NSLOT)]));
+                }
+                // ---- store (coalesced 128 B per row) and optional class max
+#pragma unroll
+                for (int j = 0; j < CC; ++j) {
+                    if (j < n) {
+                        float* __restrict__ op = prm.dst + ((size_t)(b * C + c0 + j) * H + yw) * prm.dst_pitch + x;
+                        unsigned mx = 0u;
+#pragma unroll
+                        for (int i = 0; i < R; ++i) {
+                            if (xok && yw + i < H) {
+                                op[(size_t)i * prm.dst_pitch] = acc[j][i];
+                                mx = max(mx, ordered_from_float(acc[j][i]));
+                            }
+                        }
+                        if (prm.cls_max != nullptr) {
+                            mx = __reduce_max_sync(0xffffffffu, mx);
+                            if (lane == 0 && mx != 0u) atomicMax(prm.cls_max + (size_t)b * C + c0 + j, mx);
+                        }
+                    }
+                }
+                PAMR_EV(8);
+            }
+        }
+#undef PAMR_EV
+    }
+
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(ctrl->tmem_base), "r"(512));
+}
+
+// Copy [planes,H,W] -> [planes,H,Wp] (Wp % 4 == 0) so that TMA's 16-byte stride rule holds.
+__global__ void repack_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int Wp, size_t rows) {
+    for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const float* __restrict__ s = src + row * W;
+        float* __restrict__ d = dst + row * Wp;
+        for (int x = threadIdx.x; x < W; x += blockDim.x) d[x] = s[x];
+    }
+    (void)H;
+}
+
+std::atomic<long long*> g_timeline{nullptr};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int make_tmap(CUtensorMap* map, const float* base, int planes, int H, int W, int pitch, int win_h) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return set_error(PAMR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * 4 * (cuuint64_t)H};
+    cuuint32_t box[3] = {(cuuint32_t)WIN_W, (cuuint32_t)win_h, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(PAMR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return PAMR_OK;
+}
+
+template <int R>
+int launch_one(const float* aff, const AffTiling& tiling, const float* src, int src_pitch, float* dst, int dst_pitch,
+               int B, int C, int H, int W, int Wt, unsigned* cls_max, int sm_count, cudaStream_t s) {
+    using C_ = Cfg<R>;
+    // function attributes are per device: set once per (kernel, device)
+    static std::atomic<int> attr_set[64];
+    int dev = 0;
+    PAMR_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 64 || attr_set[dev].load(std::memory_order_acquire) == 0) {
+        PAMR_CUDA_TRY(cudaFuncSetAttribute(propagate_sm100_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)C_::SMEM_BYTES));
+        if (dev < 64) attr_set[dev].store(1, std::memory_order_release);
+    }
+    alignas(64) CUtensorMap tmap;
+    int rc = make_tmap(&tmap, src, B * C, H, W, src_pitch, C_::WIN_H);
+    if (rc != PAMR_OK) return rc;
+    Params p;
+    p.aff = aff; p.dst = dst; p.cls_max = cls_max; p.dst_pitch = dst_pitch;
+    p.dbg = g_timeline.load(std::memory_order_relaxed);
+    static const int knob_cta = getenv("PAMR_B200_STAGGER_CTA") ? atoi(getenv("PAMR_B200_STAGGER_CTA")) : 0;
+    static const int knob_grp = getenv("PAMR_B200_STAGGER_GRP") ? atoi(getenv("PAMR_B200_STAGGER_GRP")) : 0;
+    p.stagger_cta_ns = knob_cta; p.stagger_grp_ns = knob_grp;
+    p.B = B; p.C = C; p.H = H; p.W = W;
+    p.tiles_x = (Wt + TX - 1) / TX;
+    p.tiles_y = tiling.tiles_y;
+    p.tiles_x_aff = tiling.tiles_x;
+    p.ntiles = p.tiles_x * p.tiles_y * B;
+    const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
+    propagate_sm100_kernel<R><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, p);
+    count_launch();
+    PAMR_CUDA_TRY(cudaGetLastError());
+    return PAMR_OK;
+}
+
+}  // namespace
+
+// Debug hook (not part of the public ABI): device buffer of 2 x 4096 x 2 int64 that CTA 0 of every
+// subsequent tuned launch fills with {clock64, event code} pairs; nullptr switches it off.
+extern "C" void pamr_debug_set_timeline(long long* dev_buf) { g_timeline.store(dev_buf); }
+
+// Width handled by the tuned kernel; a short remainder strip [Wt, W) goes to the strip kernel
+// so that a tile column with only a few live lanes is not paid for (W = 321 -> 10 tile columns + 1 px).
+int tuned_width(int W) {
+    const int rem = W % TX;
+    return (rem != 0 && rem <= 8) ? W - rem : W;
+}
+
+// Tiling of the tuned kernel (R rows per thread, tile = 32 x 4R) or R == 0 when it does not apply.
+AffTiling tuned_tiling(int H, int W, const Dilations& dil) {
+    static const int want[6] = {1, 2, 4, 8, 12, 24};
+    // debugging / A-B aid: PAMR_B200_FORCE_GENERIC=1 routes everything to the generic CUDA kernel
+    static const bool force_generic = []() {
+        const char* e = getenv("PAMR_B200_FORCE_GENERIC");
+        return e != nullptr && e[0] == '1';
+    }();
+    AffTiling t{0, 0, 0};
+    if (force_generic || dil.nd != 6 || W < TX || H < 8) return t;
+    for (int i = 0; i < 6; ++i)
+        if (dil.d[i] != want[i]) return t;
+    int best = 8, best_cost = 1 << 30;
+    for (int r = 8; r <= 10; ++r) {  // least padded rows; ties go to the larger strip (more register reuse)
+        const int ty = NW * r, cost = (H + ty - 1) / ty * ty;
+        if (cost <= best_cost) { best = r; best_cost = cost; }
+    }
+    t.R = best;
+    t.tiles_x = (W + TX - 1) / TX;
+    t.tiles_y = (H + NW * best - 1) / (NW * best);
+    return t;
+}
+
+int launch_repack(const float* src, float* dst, int planes, int H, int W, int Wp, cudaStream_t s) {
+    const size_t rows = (size_t)planes * H;
+    const unsigned grid = (unsigned)(rows < 148 * 16 ? rows : 148 * 16);
+    repack_kernel<<<grid, 128, 0, s>>>(src, dst, H, W, Wp, rows);
+    count_launch();
+    PAMR_CUDA_TRY(cudaGetLastError());
+    return PAMR_OK;
+}
+
+// One propagation step src -> dst with the tuned kernel over x in [0, tuned_width(W)).
+// src must have a pitch that is a multiple of 4 floats and a 16-byte aligned base.
+int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, int src_pitch, float* dst,
+                           int dst_pitch, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s) {
+    static int sm_counts[64] = {0};
+    int sm_count = (dev >= 0 && dev < 64) ? sm_counts[dev] : 0;
+    if (sm_count == 0) {
+        PAMR_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 64) sm_counts[dev] = sm_count;
+    }
+    if ((src_pitch & 3) != 0 || ((uintptr_t)src & 15) != 0)
+        return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: source pitch/base not 16-byte aligned");
+    const int Wt = tuned_width(W);
+    if (tiling.R == 8) return launch_one<8>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, cls_max, sm_count, s);
+    if (tiling.R == 9) return launch_one<9>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, cls_max, sm_count, s);
+    return launch_one<10>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, cls_max, sm_count, s);
 }
 
 }  // namespace pamr

@@ -134,11 +134,13 @@ def propagate(aff, mask, dilations, num_iter, return_class_max=False):
     if tuple(aff.shape) != (B, 8 * nd, H, W):
         raise RuntimeError("aff has shape %s, expected %s" % (tuple(aff.shape), (B, 8 * nd, H, W)))
     out = torch.empty_like(mask)
-    tmp = torch.empty_like(mask) if num_iter > 1 else None
+    L = _lib.lib()
+    nbytes = L.pamr_propagate_scratch_bytes(B, C, H, W, d, nd, int(num_iter))
+    tmp = torch.empty((nbytes,), dtype=torch.uint8, device=mask.device) if nbytes else None
     cmax = torch.empty((B, C), dtype=torch.int32, device=mask.device) if return_class_max else None
-    _lib.check(_lib.lib().pamr_propagate_f32(
-        aff.data_ptr(), mask.data_ptr(), out.data_ptr(), tmp.data_ptr() if tmp is not None else None, B, C, H, W, d, nd,
-        int(num_iter), cmax.data_ptr() if cmax is not None else None, _dev(mask), _stream(mask.device)))
+    _lib.check(L.pamr_propagate_f32(
+        aff.data_ptr(), mask.data_ptr(), out.data_ptr(), tmp.data_ptr() if tmp is not None else None, nbytes, B, C, H, W,
+        d, nd, int(num_iter), cmax.data_ptr() if cmax is not None else None, _dev(mask), _stream(mask.device)))
     return (out, cmax) if return_class_max else out
 
 
@@ -173,7 +175,7 @@ class PAMR(nn.Module):
         L = _lib.lib()
         iters = int(self.num_iter)
         out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
-        nbytes = L.pamr_forward_workspace_bytes(B, K, C, H, W, h, w, nd, iters)
+        nbytes = L.pamr_forward_workspace_bytes(B, K, C, H, W, h, w, d, nd, iters)
         # torch's caching allocator returns >= 512-byte aligned blocks
         ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=x.device)
         cmax = torch.empty((B, C), dtype=torch.int32, device=x.device) if return_class_max else None

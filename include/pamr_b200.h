@@ -77,15 +77,17 @@ int pamr_affinity_f32(const float* img, float* aff, int B, int K, int H, int W, 
  * `iters` propagation steps.  Replaces the loop pamr.py:138-140 (LocalAffinityCopy :57-75):
  *   M'[b,c,y,x] = sum_p aff[b,p,y,x] * M[b,c,clamp(y+dy_p),clamp(x+dx_p)].
  * aff [B,8*nd,H,W]; m_in [B,C,H,W] (never written); m_out [B,C,H,W] receives the result;
- * m_tmp [B,C,H,W] is scratch for the ping-pong (may be NULL when iters <= 1).
- * iters == 0 copies m_in to m_out.  m_in, m_out, m_tmp must not alias.
+ * scratch: device memory of at least pamr_propagate_scratch_bytes(...) bytes, 256-byte aligned,
+ * for the ping-pong buffers (rows pitched to 16 bytes for TMA); may be NULL when that is 0.
+ * iters == 0 copies m_in to m_out.  m_in, m_out and scratch must not overlap.
  * cls_max: NULL, or [B,C] unsigned that receives the per-(b,c) maximum of the RESULT in the
  * ordered encoding of pamr_ordered_from_float() (fused into the last step; saves the max pass of
  * pseudo_gtmask, SoftMaxAE.py:35, when no resize follows).  The call initialises it.
  */
-int pamr_propagate_f32(const float* aff, const float* m_in, float* m_out, float* m_tmp, int B, int C,
-                       int H, int W, const int* dilations, int nd, int iters, unsigned* cls_max,
-                       int dev, pamr_stream_t stream);
+size_t pamr_propagate_scratch_bytes(int B, int C, int H, int W, const int* dilations, int nd, int iters);
+int pamr_propagate_f32(const float* aff, const float* m_in, float* m_out, void* scratch, size_t scratch_bytes,
+                       int B, int C, int H, int W, const int* dilations, int nd, int iters,
+                       unsigned* cls_max, int dev, pamr_stream_t stream);
 
 /*
  * PAMR(num_iter, dilations).forward(img, mask)  (pamr.py:124-143) in one call:
@@ -93,7 +95,8 @@ int pamr_propagate_f32(const float* aff, const float* m_in, float* m_out, float*
  * `iters` propagation steps into out [B,C,H,W].  workspace: device scratch of at least
  * pamr_forward_workspace_bytes(...) bytes, 256-byte aligned.
  */
-size_t pamr_forward_workspace_bytes(int B, int K, int C, int H, int W, int h, int w, int nd, int iters);
+size_t pamr_forward_workspace_bytes(int B, int K, int C, int H, int W, int h, int w, const int* dilations,
+                                    int nd, int iters);
 int pamr_forward_f32(const float* img, const float* mask, float* out, void* workspace,
                      size_t workspace_bytes, int B, int K, int C, int H, int W, int h, int w,
                      const int* dilations, int nd, int iters, unsigned* cls_max, int dev,

@@ -217,9 +217,9 @@ int pamr_forward_f32(const float* img, const float* mask, float* out, void* work
         PAMR_TRY(launch_resize_bilinear(mask, rs, B * C, h, w, H, W, s));  // pamr.py:125
         m0 = rs;
     }
-    PAMR_TRY(launch_affinity(img, aff, B, K, H, W, dil, plan.tiling, s));  // pamr.py:132-136
-    return launch_propagate(aff, plan.tiling.R > 0, m0, out, scratch, plan.scratch_bytes, B, C, H, W, dil, iters, cls_max,
-                            dev, s);  // pamr.py:138-140
+    // pamr.py:132-136 (affinity) and :138-140 (propagation loop)
+    return launch_affinity_propagate(img, K, aff, nullptr, false, m0, out, scratch, plan.scratch_bytes, B, C, H, W, dil,
+                                     iters, cls_max, dev, s);
 }
 
 int pamr_clean_f32(const float* m, const float* labels, float* cleaned, unsigned* cls_max, int B, int C, int h, int w,
@@ -289,10 +289,10 @@ int pamr_pseudo_labels_host_f32(const float* h_img, const float* h_mask, const f
             PAMR_TRY(launch_resize_bilinear(im, (float*)(d + o_ims), B * K, H, W, h, w, s));
             im = (const float*)(d + o_ims);
         }
-        PAMR_TRY(launch_affinity(im, (float*)(d + o_aff), B, K, h, w, dil, tiling, s));
         unsigned* mx = (unsigned*)(d + o_max);
-        PAMR_TRY(launch_propagate((const float*)(d + o_aff), tiling.R > 0, (const float*)(d + o_mask), (float*)(d + o_a), d + o_b,
-                                  n_scr, B, C, h, w, dil, iters, resize ? nullptr : mx, dev, s));
+        PAMR_TRY(launch_affinity_propagate(im, K, (float*)(d + o_aff), nullptr, false, (const float*)(d + o_mask),
+                                           (float*)(d + o_a), d + o_b, n_scr, B, C, h, w, dil, iters,
+                                           resize ? nullptr : mx, dev, s));
         const float* lab = (h_labels && C > 1) ? (const float*)(d + o_lab) : nullptr;
         if (resize) PAMR_TRY(launch_clean((const float*)(d + o_a), lab, nullptr, mx, B, C, h, w, H, W, s));
         PAMR_TRY(launch_pseudo_labels((const float*)(d + o_a), lab, mx, (uint8_t*)(d + o_out), nullptr, nullptr, B, C, h,

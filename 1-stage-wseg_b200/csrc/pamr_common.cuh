@@ -106,6 +106,9 @@ size_t propagate_scratch_bytes(int B, int C, int H, int W, const Dilations& dil,
 int launch_propagate(const float* aff, bool aff_is_tiled, const float* m_in, float* m_out, void* scratch,
                      size_t scratch_bytes, int B, int C, int H, int W, const Dilations& dil, int iters,
                      unsigned* cls_max, int dev, cudaStream_t s);
+int launch_affinity_propagate(const float* img, int K, float* aff_out, const float* aff_in, bool aff_is_tiled,
+                              const float* m_in, float* m_out, void* scratch, size_t scratch_bytes, int B, int C, int H,
+                              int W, const Dilations& dil, int iters, unsigned* cls_max, int dev, cudaStream_t s);
 int launch_clean(const float* m, const float* labels, float* cleaned, unsigned* cls_max, int B, int C, int h, int w,
                  int H, int W, cudaStream_t s);
 int launch_pseudo_labels(const float* m, const float* labels, const unsigned* cls_max, uint8_t* label,

@@ -159,16 +159,61 @@ ScratchPlan plan_scratch(int B, int C, int H, int W, const Dilations& dil, int i
 
 }  // namespace
 
+// Fork/join helper: a per-thread, per-device side stream on which small independent kernels
+// (row repack, remainder strip) run concurrently with the big kernel on the caller's stream.
+// The persistent propagation kernel occupies every SM with one CTA but leaves threads and
+// registers for these, so their time disappears from the critical path.
+struct ForkJoin {
+    cudaStream_t main_s = nullptr, side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int init(int dev, cudaStream_t m) {
+        static thread_local cudaStream_t cache[64] = {nullptr};
+        main_s = m;
+        if (dev >= 0 && dev < 64 && cache[dev] != nullptr) {
+            side = cache[dev];
+        } else {
+            PAMR_CUDA_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+            if (dev >= 0 && dev < 64) cache[dev] = side;
+        }
+        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        return PAMR_OK;
+    }
+    int fork() {  // work enqueued on `side` after this sees everything enqueued on main so far
+        PAMR_CUDA_TRY(cudaEventRecord(ev_fork, main_s));
+        PAMR_CUDA_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
+        return PAMR_OK;
+    }
+    int join() {  // work enqueued on main after this sees everything enqueued on `side` so far
+        PAMR_CUDA_TRY(cudaEventRecord(ev_join, side));
+        PAMR_CUDA_TRY(cudaStreamWaitEvent(main_s, ev_join, 0));
+        return PAMR_OK;
+    }
+    ~ForkJoin() {
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+    }
+};
+
 size_t propagate_scratch_bytes(int B, int C, int H, int W, const Dilations& dil, int iters, bool aff_is_tiled) {
     return plan_scratch(B, C, H, W, dil, iters, aff_is_tiled).total;
 }
 
-int launch_propagate(const float* aff, bool aff_is_tiled, const float* m_in, float* m_out, void* scratch,
-                     size_t scratch_bytes, int B, int C, int H, int W, const Dilations& dil, int iters,
-                     unsigned* cls_max, int dev, cudaStream_t s) {
+// Affinity (optional) + `iters` propagation steps.  When img != nullptr the affinity is computed
+// here into `aff` (tile-major if the tuned kernel applies, see tuned_tiling), concurrently with the
+// repack of the input mask; otherwise `aff` is an input (standard layout unless aff_is_tiled).
+int launch_affinity_propagate(const float* img, int K, float* aff_out, const float* aff_in, bool aff_is_tiled,
+                              const float* m_in, float* m_out, void* scratch, size_t scratch_bytes, int B, int C, int H,
+                              int W, const Dilations& dil, int iters, unsigned* cls_max, int dev, cudaStream_t s) {
     const size_t N = (size_t)B * C * H * W;
+    const AffTiling tiling = tuned_tiling(H, W, dil);
+    const bool tuned = tiling.R > 0;
     if (cls_max != nullptr) PAMR_CUDA_TRY(cudaMemsetAsync(cls_max, 0, sizeof(unsigned) * (size_t)B * C, s));
     if (iters <= 0) {
+        if (img != nullptr) {
+            int rc = launch_affinity(img, aff_out, B, K, H, W, dil, tiling, s);  // the caller asked for it
+            if (rc != PAMR_OK) return rc;
+        }
         PAMR_CUDA_TRY(cudaMemcpyAsync(m_out, m_in, N * sizeof(float), cudaMemcpyDeviceToDevice, s));
         if (cls_max != nullptr) {
             dim3 grid((unsigned)min((size_t)64, ((size_t)H * W + 255) / 256), B * C);
@@ -178,6 +223,7 @@ int launch_propagate(const float* aff, bool aff_is_tiled, const float* m_in, flo
         }
         return PAMR_OK;
     }
+    if (img != nullptr) aff_is_tiled = tuned;
     const ScratchPlan plan = plan_scratch(B, C, H, W, dil, iters, aff_is_tiled);
     if (scratch == nullptr || scratch_bytes < plan.total)
         return set_error(PAMR_ERR_WORKSPACE, "propagate: scratch of %zu bytes given, %zu needed", scratch_bytes,
@@ -186,38 +232,52 @@ int launch_propagate(const float* aff, bool aff_is_tiled, const float* m_in, flo
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: scratch must be 256-byte aligned");
     const int Wp = (int)align_up((size_t)W, 4);
     float* P[2] = {(float*)scratch, (float*)((char*)scratch + plan.pingpong_each)};
-    const AffTiling tiling = tuned_tiling(H, W, dil);
-    const bool tuned = tiling.R > 0;
     if (!tuned && aff_is_tiled)
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: tiled affinity without the tuned kernel");
-    if (tuned && !aff_is_tiled) {
-        float* at = (float*)((char*)scratch + 2 * plan.pingpong_each);
-        int rc = launch_aff_relayout(aff, at, B, H, W, tiling, s);
-        if (rc != PAMR_OK) return rc;
-        aff = at;
-    }
     const int Wt = tuned ? tuned_width(W) : 0;
+    const bool need_repack = tuned && ((W & 3) != 0 || ((uintptr_t)m_in & 15) != 0);
+    const bool need_strip = tuned && Wt < W;
 
+    ForkJoin fj;
+    if (need_repack || need_strip) {
+        int rc = fj.init(dev, s);
+        if (rc != PAMR_OK) return rc;
+    }
     const float* src = m_in;
     int src_pitch = W;
     int next = 0;  // next free ping-pong buffer
-    if (tuned && ((W & 3) != 0 || ((uintptr_t)m_in & 15) != 0)) {
-        int rc = launch_repack(m_in, P[0], B * C, H, W, Wp, s);
-        if (rc != PAMR_OK) return rc;
+    int rc = PAMR_OK;
+    if (need_repack) {  // on the side stream, concurrently with the affinity / relayout kernel
+        if ((rc = fj.fork()) != PAMR_OK) return rc;
+        if ((rc = launch_repack(m_in, P[0], B * C, H, W, Wp, fj.side)) != PAMR_OK) return rc;
         src = P[0];
         src_pitch = Wp;
         next = 1;
     }
+    const float* aff = aff_in;
+    if (img != nullptr) {
+        if ((rc = launch_affinity(img, aff_out, B, K, H, W, dil, tiling, s)) != PAMR_OK) return rc;
+        aff = aff_out;
+    } else if (tuned && !aff_is_tiled) {
+        float* at = (float*)((char*)scratch + 2 * plan.pingpong_each);
+        if ((rc = launch_aff_relayout(aff_in, at, B, H, W, tiling, s)) != PAMR_OK) return rc;
+        aff = at;
+    }
+    if (need_repack && (rc = fj.join()) != PAMR_OK) return rc;
+
     for (int it = 0; it < iters; ++it) {
         const bool last = (it == iters - 1);
         float* dst = last ? m_out : P[next];
         const int dst_pitch = last ? W : Wp;
         unsigned* mx = last ? cls_max : nullptr;
-        int rc;
         if (tuned) {
+            if (need_strip) {  // remainder columns on the side stream, concurrently with the tiles
+                if ((rc = fj.fork()) != PAMR_OK) return rc;
+                rc = launch_strip(aff, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, mx, fj.side);
+                if (rc != PAMR_OK) return rc;
+            }
             rc = launch_propagate_tuned(aff, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, mx, dev, s);
-            if (rc == PAMR_OK && Wt < W)
-                rc = launch_strip(aff, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, mx, s);
+            if (rc == PAMR_OK && need_strip) rc = fj.join();
         } else {
             rc = launch_generic(aff, src, src_pitch, dst, dst_pitch, B, C, H, W, dil, mx, s);
         }
@@ -227,6 +287,13 @@ int launch_propagate(const float* aff, bool aff_is_tiled, const float* m_in, flo
         next ^= 1;
     }
     return PAMR_OK;
+}
+
+int launch_propagate(const float* aff, bool aff_is_tiled, const float* m_in, float* m_out, void* scratch,
+                     size_t scratch_bytes, int B, int C, int H, int W, const Dilations& dil, int iters,
+                     unsigned* cls_max, int dev, cudaStream_t s) {
+    return launch_affinity_propagate(nullptr, 0, nullptr, aff, aff_is_tiled, m_in, m_out, scratch, scratch_bytes, B, C, H,
+                                     W, dil, iters, cls_max, dev, s);
 }
 
 }  // namespace pamr

@@ -133,7 +133,6 @@ struct Cfg {
 
 struct Ctrl {  // lives in the last 1 KB of dynamic shared memory
     unsigned long long tma_bar[NSLOT];
-    unsigned long long ready_bar[NSLOT];
     unsigned long long empty_bar[NSLOT];
     uint32_t tmem_base;
 };
@@ -143,6 +142,8 @@ struct Params {
     float* dst;        // [B,C,H,dst_pitch]
     unsigned* cls_max; // [B,C] or nullptr
     int stagger_cta_ns, stagger_grp_ns;  // experiment knobs (env PAMR_B200_STAGGER_CTA / _GRP)
+    int dbg_cta;       // CTA that records the timeline
+    int pf_class;      // class index at whose TMA issue the next tile's weights are prefetched into L2 (-1: never)
     long long* dbg;    // nullptr, or timeline buffer (debug hook pamr_debug_set_timeline): 2 x 4096 x {clock, code}
     int dst_pitch;
     int B, C, H, W;
@@ -159,7 +160,9 @@ struct Params {
 // one (rolled) copy of the code: the unrolled loop body must stay inside the 32 KB instruction cache.
 template <int R>
 struct TmemLayout {
-    static constexpr int CPAD = (12 * R + WB - 1) / WB * WB;  // centre columns padded to a batch
+    static constexpr int RS = (R + 1) / 2 * 2;                 // columns per tap: R rounded up to even, so
+                                                               // that row pairs (i, i+1) are aligned register pairs
+    static constexpr int CPAD = (12 * RS + WB - 1) / WB * WB;  // centre columns padded to a batch
     static constexpr int SIDE0 = CPAD;
     static constexpr int NCOLS = CPAD + 12 * 32;              // <= 512
     static_assert(NCOLS <= 512, "TMEM columns");
@@ -167,7 +170,8 @@ struct TmemLayout {
 
 template <int R>
 __host__ __device__ constexpr int seq_col(int s) {
-    return (s < 12) ? s * R : TmemLayout<R>::SIDE0 + ((s - 12) / 3) * 32 + ((s - 12) % 3) * R;
+    return (s < 12) ? s * TmemLayout<R>::RS
+                    : TmemLayout<R>::SIDE0 + ((s - 12) / 3) * 32 + ((s - 12) % 3) * TmemLayout<R>::RS;
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
@@ -230,7 +234,7 @@ __device__ __forceinline__ void compute_pass(const float* (&sp)[CC], uint32_t tb
 #ifdef PAMR_NO_FFMA2
     constexpr bool kPacked = false;
 #else
-    constexpr bool kPacked = (R % 2 == 0);
+    constexpr bool kPacked = true;  // odd R: the last row stays scalar
 #endif
     constexpr int NCB = L::CPAD / WB;  // centre batches
     float wc[2][WB];
@@ -253,7 +257,7 @@ __device__ __forceinline__ void compute_pass(const float* (&sp)[CC], uint32_t tb
                 for (int n = 0; n < N; ++n) v[n][r + HALO] = sp[n][r * WIN_W];
             }
         }
-        int q = 0;  // compile-time after full unrolling
+        int bcur = -1;  // weight batch currently held (compile-time after full unrolling)
 #pragma unroll
         for (int id = 0; id < 6; ++id) {
             const int d = dil_of(id);
@@ -261,24 +265,24 @@ __device__ __forceinline__ void compute_pass(const float* (&sp)[CC], uint32_t tb
             for (int a = -1; a <= 1; a += 2) {
 #pragma unroll
                 for (int i = 0; i < R; ++i) {
-                    const bool pair = kPacked && (d % 2 == 0);  // rows (i, i+1) as one FFMA2
-                    if (pair && (i % 2 == 1)) continue;          // odd row handled with its even partner
-                    if (q % WB == 0) {  // batch boundary: wait for this batch, prefetch the next one
-                        tmem_wait_ld(wc[(q / WB) & 1]);
-                        if (q / WB + 1 < NCB) tmem_ld16(tbase + (q / WB + 1) * WB, wc[(q / WB + 1) & 1]);
+                    const bool pair = kPacked && (d % 2 == 0) && (i + 1 < R || i % 2 == 1);  // rows (i, i+1) as one FFMA2
+                    if (pair && (i % 2 == 1)) continue;  // odd row handled with its even partner
+                    const int q = (2 * id + (a > 0 ? 1 : 0)) * L::RS + i;
+                    if (q / WB != bcur) {  // batch boundary: wait for this batch, prefetch the next one
+                        bcur = q / WB;
+                        tmem_wait_ld(wc[bcur & 1]);
+                        if (bcur + 1 < NCB) tmem_ld16(tbase + (bcur + 1) * WB, wc[(bcur + 1) & 1]);
                         else tmem_ld32(tbase + L::SIDE0, ws[0]);  // first side group
                     }
                     if (pair) {
 #pragma unroll
                         for (int n = 0; n < N; ++n)
-                            fma2(acc[n][i], acc[n][i + 1], wc[(q / WB) & 1][q % WB], wc[(q / WB) & 1][q % WB + 1],
+                            fma2(acc[n][i], acc[n][i + 1], wc[bcur & 1][q % WB], wc[bcur & 1][q % WB + 1],
                                  v[n][i + a * d + HALO], v[n][i + 1 + a * d + HALO]);
-                        q += 2;
                     } else {
-                        const float w = wc[(q / WB) & 1][q % WB];
+                        const float w = wc[bcur & 1][q % WB];
 #pragma unroll
                         for (int n = 0; n < N; ++n) acc[n][i] = fmaf(w, v[n][i + a * d + HALO], acc[n][i]);
-                        ++q;
                     }
                 }
             }
@@ -310,15 +314,15 @@ __device__ __forceinline__ void compute_pass(const float* (&sp)[CC], uint32_t tb
             for (int a = -1; a <= 1; ++a) {
 #pragma unroll
                 for (int i = 0; i < R; ++i) {
-                    const bool pair = kPacked && ((a * d) % 2 == 0);  // rows (i, i+1) as one FFMA2
+                    const bool pair = kPacked && ((a * d) % 2 == 0) && (i + 1 < R || i % 2 == 1);  // rows (i, i+1)
                     if (pair && (i % 2 == 1)) continue;
                     if (pair) {
 #pragma unroll
                         for (int n = 0; n < N; ++n)
-                            fma2(acc[n][i], acc[n][i + 1], w[(a + 1) * R + i], w[(a + 1) * R + i + 1], v[n][i + a * d + HALO],
-                                 v[n][i + 1 + a * d + HALO]);
+                            fma2(acc[n][i], acc[n][i + 1], w[(a + 1) * L::RS + i], w[(a + 1) * L::RS + i + 1],
+                                 v[n][i + a * d + HALO], v[n][i + 1 + a * d + HALO]);
                     } else {
-                        const float wv = w[(a + 1) * R + i];
+                        const float wv = w[(a + 1) * L::RS + i];
 #pragma unroll
                         for (int n = 0; n < N; ++n) acc[n][i] = fmaf(wv, v[n][i + a * d + HALO], acc[n][i]);
                     }
@@ -334,44 +338,46 @@ __device__ __forceinline__ bool needs_patch(int x0, int y0, int H, int W) {
 }
 
 // Border tiles: TMA zero-filled everything outside the image; overwrite it with the clamped
-// (replicate-padded) value.  Window element (wy,wx) <-> image pixel (y0-24+wy, x0-24+wx).
+// (replicate-padded, pamr.py:50) value.  Window element (wy,wx) <-> image pixel (y0-24+wy, x0-24+wx).
+// Executed by the NW warps of the compute group that is about to read the slot (wq = warp in group).
+// Every store targets an out-of-image element and every load an in-image one, so the four warps
+// need no ordering among themselves; the caller synchronises the group afterwards.
 template <int R>
-__device__ __forceinline__ void patch_window(float* slot, int x0, int y0, int H, int W, int lane) {
+__device__ __forceinline__ void patch_window(float* slot, int x0, int y0, int H, int W, int wq, int lane) {
     constexpr int WIN_H = Cfg<R>::WIN_H;
-    const int vx0 = max(0, HALO - x0), vx1 = min(WIN_W, W - x0 + HALO);
-    const int vy0 = max(0, HALO - y0), vy1 = min(WIN_H, H - y0 + HALO);
-    if (vx0 == 0 && vx1 == WIN_W && vy0 == 0 && vy1 == WIN_H) return;
-    // left / right columns of the valid rows: one broadcast read + one store per row and side
+    const int vx0 = max(0, HALO - x0), vx1 = min(WIN_W, W - x0 + HALO);  // in-image columns [vx0, vx1)
+    const int vy0 = max(0, HALO - y0), vy1 = min(WIN_H, H - y0 + HALO);  // in-image rows    [vy0, vy1)
+    // rows above / below the image: full width; the source row (first / last in-image row, columns
+    // clamped) is read once and then stored to every row this warp owns
+#pragma unroll
+    for (int k = 0; k < (WIN_W + 31) / 32; ++k) {
+        const int wx = 32 * k + lane;
+        if (wx < WIN_W) {
+            const int sx = min(max(wx, vx0), vx1 - 1);
+            if (vy0 > 0) {
+                const float v = slot[vy0 * WIN_W + sx];
+                for (int wy = wq; wy < vy0; wy += NW) slot[wy * WIN_W + wx] = v;
+            }
+            if (vy1 < WIN_H) {
+                const float v = slot[(vy1 - 1) * WIN_W + sx];
+                for (int wy = vy1 + wq; wy < WIN_H; wy += NW) slot[wy * WIN_W + wx] = v;
+            }
+        }
+    }
+    // in-image rows: columns left / right of the image (one broadcast read per row and side)
     if (vx0 > 0) {
 #pragma unroll 4
-        for (int wy = vy0; wy < vy1; ++wy) {
+        for (int wy = vy0 + wq; wy < vy1; wy += NW) {
             const float v = slot[wy * WIN_W + vx0];
             if (lane < vx0) slot[wy * WIN_W + lane] = v;
         }
     }
     if (vx1 < WIN_W) {
 #pragma unroll 4
-        for (int wy = vy0; wy < vy1; ++wy) {
+        for (int wy = vy0 + wq; wy < vy1; wy += NW) {
             const float v = slot[wy * WIN_W + vx1 - 1];
             if (vx1 + lane < WIN_W) slot[wy * WIN_W + vx1 + lane] = v;
             if (vx1 + 32 + lane < WIN_W) slot[wy * WIN_W + vx1 + 32 + lane] = v;
-        }
-    }
-    if (vy0 == 0 && vy1 == WIN_H) return;
-    __syncwarp();
-    // rows above / below: replicate the (already side-patched) first / last valid row
-#pragma unroll
-    for (int k = 0; k < (WIN_W + 31) / 32; ++k) {
-        const int wx = 32 * k + lane;
-        if (wx < WIN_W) {
-            if (vy0 > 0) {
-                const float v = slot[vy0 * WIN_W + wx];
-                for (int wy = 0; wy < vy0; ++wy) slot[wy * WIN_W + wx] = v;
-            }
-            if (vy1 < WIN_H) {
-                const float v = slot[(vy1 - 1) * WIN_W + wx];
-                for (int wy = vy1; wy < WIN_H; ++wy) slot[wy * WIN_W + wx] = v;
-            }
         }
     }
 }
@@ -395,7 +401,6 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSLOT; ++s) {
             mbar_init(smem_u32(&ctrl->tma_bar[s]), 1);
-            mbar_init(smem_u32(&ctrl->ready_bar[s]), 1);
             mbar_init(smem_u32(&ctrl->empty_bar[s]), NW);  // the NW warps of the group that read the slot
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -412,62 +417,42 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
     const int tiles_per_img = prm.tiles_x * prm.tiles_y;
 
     if (warp == NWC) {
-        // ===================== producer warp: TMA issue + border patch =====================
-        // Sequence number n = (tile_iter, class) -> slot n % NSLOT.  A consumer waits for tma_bar
-        // (bytes landed) and ready_bar (halo patched).  For interior tiles ready_bar is signalled
-        // right at issue time, so the producer is not on the consumers' critical path.
+        // ===================== producer warp: TMA issue =====================
+        // Sequence number n = (tile_iter, class) -> slot n % NSLOT.  A consumer group waits for
+        // tma_bar (bytes landed), patches the halo itself if the tile touches the image border,
+        // computes, and releases the slot through empty_bar.
         const long long total = (long long)my_tiles * C;
-        long long n_issue = 0, n_done = 0;
-        while (n_done < total) {
-            int did = 0, x0 = 0, y0 = 0;
-            if (n_issue < total) {
-                const int s = (int)(n_issue % NSLOT);
-                const uint32_t round = (uint32_t)(n_issue / NSLOT);
-                const int ti = (int)(n_issue / C), c = (int)(n_issue % C);
-                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-                const int b = tile / tiles_per_img, t = tile % tiles_per_img;
-                x0 = (t % prm.tiles_x) * TX, y0 = (t / prm.tiles_x) * C_::TY;
-                const bool border = needs_patch<R>(x0, y0, H, W);
-                if (lane == 0 && mbar_poll(smem_u32(&ctrl->empty_bar[s]), (round & 1u) ^ 1u)) {
-                    const uint32_t bar = smem_u32(&ctrl->tma_bar[s]);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive_expect_tx(bar, C_::SLOT_BYTES);
-                    tma_load_3d(smem_u32(slots + (size_t)s * C_::SLOT_FLOATS), &tmap, bar, x0 - HALO, y0 - HALO, b * C + c);
-                    if (!border) mbar_arrive(smem_u32(&ctrl->ready_bar[s]));
-                    did = 1;
-                }
-                did = __shfl_sync(0xffffffffu, did, 0);
-                if (did) {
-                    ++n_issue;
+        int pn = 0;
+        for (long long n_issue = 0; n_issue < total; ++n_issue) {
+            const int s = (int)(n_issue % NSLOT);
+            const uint32_t round = (uint32_t)(n_issue / NSLOT);
+            const int ti = (int)(n_issue / C), c = (int)(n_issue % C);
+            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int b = tile / tiles_per_img, t = tile % tiles_per_img;
+            const int x0 = (t % prm.tiles_x) * TX, y0 = (t / prm.tiles_x) * C_::TY;
+            if (lane == 0) {
+                mbar_wait(smem_u32(&ctrl->empty_bar[s]), (round & 1u) ^ 1u);
+                const uint32_t bar = smem_u32(&ctrl->tma_bar[s]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive_expect_tx(bar, C_::SLOT_BYTES);
+                tma_load_3d(smem_u32(slots + (size_t)s * C_::SLOT_FLOATS), &tmap, bar, x0 - HALO, y0 - HALO, b * C + c);
+                if (prm.dbg != nullptr && (int)blockIdx.x == prm.dbg_cta && pn < 4096) {  // timeline: issue time of class n
+                    prm.dbg[(2 * 4096 + pn) * 2] = clock64();
+                    prm.dbg[(2 * 4096 + pn) * 2 + 1] = 1000 + n_issue;
+                    ++pn;
                 }
             }
-            // skip over interior-tile entries (nothing to patch, ready already signalled)
-            while (n_done < n_issue) {
-                const int ti = (int)(n_done / C);
-                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-                const int t = tile % tiles_per_img;
-                const int px0 = (t % prm.tiles_x) * TX, py0 = (t / prm.tiles_x) * C_::TY;
-                if (needs_patch<R>(px0, py0, H, W)) break;
-                ++n_done;
+            // Late in a tile, pull the NEXT tile's affinity weights (one contiguous 48*R*128-byte block
+            // per lane quarter of the tile-major layout) from HBM into L2, so that the TMEM fill at the
+            // tile boundary -- when every SM asks for its weights at once -- mostly hits L2.
+            if (c == prm.pf_class && ti + 1 < my_tiles && lane < 4) {
+                const int ntile = (int)blockIdx.x + (ti + 1) * (int)gridDim.x;
+                const int nb = ntile / tiles_per_img, nt = ntile % tiles_per_img;
+                const float* wp = prm.aff + (((((size_t)nb * prm.tiles_y + nt / prm.tiles_x) * prm.tiles_x_aff +
+                                               nt % prm.tiles_x) * 4 + lane) * 48 * R) * 32;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wp), "r"(48 * R * 32 * 4) : "memory");
             }
-            if (n_done < n_issue) {
-                const int s = (int)(n_done % NSLOT);
-                const uint32_t round = (uint32_t)(n_done / NSLOT);
-                int landed = (lane == 0) ? (int)mbar_poll(smem_u32(&ctrl->tma_bar[s]), round & 1u) : 0;
-                landed = __shfl_sync(0xffffffffu, landed, 0);
-                if (landed) {
-                    const int ti = (int)(n_done / C);
-                    const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-                    const int t = tile % tiles_per_img;
-                    patch_window<R>(slots + (size_t)s * C_::SLOT_FLOATS, (t % prm.tiles_x) * TX, (t / prm.tiles_x) * C_::TY,
-                                    H, W, lane);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&ctrl->ready_bar[s]));
-                    ++n_done;
-                    did = 1;
-                }
-            }
-            if (!did) __nanosleep(32);  // do not steal issue slots from the compute warp on this SMSP
+            __syncwarp();
         }
     } else {
         // ===================== compute warps: 2 groups x NW warps =====================
@@ -477,7 +462,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         if ((blockIdx.x & 1) && prm.stagger_cta_ns > 0) __nanosleep(prm.stagger_cta_ns);
 #define PAMR_EV(code)                                                                         \
     do {                                                                                      \
-        if (prm.dbg != nullptr && blockIdx.x == 0 && grp < 2 && wq == 0 && lane == 0 && dn < 4096) {      \
+        if (prm.dbg != nullptr && (int)blockIdx.x == prm.dbg_cta && grp < 2 && wq == 0 && lane == 0 && dn < 4096) {      \
             prm.dbg[((grp & 1) * 4096 + dn) * 2] = clock64();                                        \
             prm.dbg[((grp & 1) * 4096 + dn) * 2 + 1] = (code);                                       \
             ++dn;                                                                             \
@@ -490,6 +475,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             const int x = x0 + lane, yw = y0 + wq * R;
             const bool xok = x < W;
             const long long seq0 = (long long)ti * C;
+            const bool border = needs_patch<R>(x0, y0, H, W);
 
             // ---- park the tile's 48*R weights per thread in TMEM (layout: TmemLayout); each group
             //      loads half of the taps for the lanes it shares with its sibling warp
@@ -528,20 +514,22 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             PAMR_EV(4);
             if (grp != 0 && prm.stagger_grp_ns > 0) __nanosleep(prm.stagger_grp_ns * grp);
 
+            int probe = 0;  // 1: the barriers of this group's next class were already seen complete
             for (int k = grp; k < C; k += NG) {
                 const int c0 = k, n = 1;
-                const float* sp[CC];
+                const long long sq = seq0 + k;
+                const int s = (int)(sq % NSLOT);
+                const uint32_t par = (uint32_t)(sq / NSLOT) & 1u;
                 PAMR_EV(100 + k);
-#pragma unroll
-                for (int j = 0; j < CC; ++j) {
-                    const long long sq = seq0 + c0 + (j < n ? j : 0);
-                    const int s = (int)(sq % NSLOT);
-                    if (j < n) {
-                        mbar_wait(smem_u32(&ctrl->tma_bar[s]), (uint32_t)(sq / NSLOT) & 1u);
-                        mbar_wait(smem_u32(&ctrl->ready_bar[s]), (uint32_t)(sq / NSLOT) & 1u);
-                    }
-                    sp[j] = slots + (size_t)s * C_::SLOT_FLOATS + (wq * R + HALO) * WIN_W + lane + HALO;
+                if (!probe) mbar_wait(smem_u32(&ctrl->tma_bar[s]), par);  // bytes landed
+                if (border) {  // replicate padding: the group patches the halo of its own slot
+                    patch_window<R>(slots + (size_t)s * C_::SLOT_FLOATS, x0, y0, H, W, wq, lane);
+                    asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(NW * 32) : "memory");
                 }
+                const float* sp[CC];
+#pragma unroll
+                for (int j = 0; j < CC; ++j)
+                    sp[j] = slots + (size_t)s * C_::SLOT_FLOATS + (wq * R + HALO) * WIN_W + lane + HALO;
                 PAMR_EV(6);
                 float acc[CC][R];
 #pragma unroll
@@ -549,14 +537,21 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
 #pragma unroll
                     for (int i = 0; i < R; ++i) acc[j][i] = 0.f;
                 compute_pass<R, 1>(sp, tbase, acc);
-                // release the slots as early as possible
+                PAMR_EV(9);
+                // release the slot as early as possible
                 __syncwarp();
-                PAMR_EV(7);
-                if (lane == 0) {
-#pragma unroll
-                    for (int j = 0; j < CC; ++j)
-                        if (j < n) mbar_arrive(smem_u32(&ctrl->empty_bar[(int)((seq0 + c0 + j) % NSLOT)]));
+                if (lane == 0) mbar_arrive(smem_u32(&ctrl->empty_bar[s]));
+                // Probe the next class's barriers now, without blocking: an mbarrier test takes a few
+                // hundred cycles when the LSU queues are full of LDS, and that latency then overlaps the
+                // stores below instead of sitting at the head of the next pass.
+                probe = 0;
+                if (k + NG < C) {
+                    const long long sq2 = sq + NG;
+                    const int s2 = (int)(sq2 % NSLOT);
+                    const uint32_t par2 = (uint32_t)(sq2 / NSLOT) & 1u;
+                    probe = (int)mbar_poll(smem_u32(&ctrl->tma_bar[s2]), par2);
                 }
+                PAMR_EV(7);
                 // ---- store (coalesced 128 B per row) and optional class max
 #pragma unroll
                 for (int j = 0; j < CC; ++j) {
@@ -652,6 +647,10 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
     static const int knob_cta = getenv("PAMR_B200_STAGGER_CTA") ? atoi(getenv("PAMR_B200_STAGGER_CTA")) : 0;
     static const int knob_grp = getenv("PAMR_B200_STAGGER_GRP") ? atoi(getenv("PAMR_B200_STAGGER_GRP")) : 0;
     p.stagger_cta_ns = knob_cta; p.stagger_grp_ns = knob_grp;
+    // default: prefetch the next tile's weights when the third-last class is issued (PAMR_B200_PF_CLASS overrides)
+    static const int knob_pf = getenv("PAMR_B200_PF_CLASS") ? atoi(getenv("PAMR_B200_PF_CLASS")) : -2;
+    p.pf_class = (knob_pf == -2) ? (C >= 3 ? C - 3 : 0) : (knob_pf < C ? knob_pf : -1);
+    p.dbg_cta = getenv("PAMR_B200_DBG_CTA") ? atoi(getenv("PAMR_B200_DBG_CTA")) : 0;
     p.B = B; p.C = C; p.H = H; p.W = W;
     p.tiles_x = (Wt + TX - 1) / TX;
     p.tiles_y = tiling.tiles_y;
@@ -689,11 +688,18 @@ AffTiling tuned_tiling(int H, int W, const Dilations& dil) {
     if (force_generic || dil.nd != 6 || W < TX || H < 8) return t;
     for (int i = 0; i < 6; ++i)
         if (dil.d[i] != want[i]) return t;
-    int best = 8, best_cost = 1 << 30;
-    for (int r = 8; r <= 10; ++r) {  // least padded rows; ties go to the larger strip (more register reuse)
-        const int ty = NW * r, cost = (H + ty - 1) / ty * ty;
-        if (cost <= best_cost) { best = r; best_cost = cost; }
+    // Rows per thread: the packed-FFMA2 body needs an even R (measured cycles per pixel-class:
+    // R=10 1.11, R=8 1.19; the scalar R=9 body is ~2x slower), so pick the even R with the
+    // least (padded rows x cost per row).  PAMR_B200_ROWS=8|9|10 overrides (experiments).
+    static const int force_rows = getenv("PAMR_B200_ROWS") ? atoi(getenv("PAMR_B200_ROWS")) : 0;
+    int best = 10;
+    double best_cost = 1e30;
+    for (int r = 8; r <= 10; ++r) {
+        const int ty = NW * r;
+        const double cost = (double)((H + ty - 1) / ty * ty) * (r == 10 ? 1.11 : r == 9 ? 1.13 : 1.19);
+        if (cost < best_cost) { best = r; best_cost = cost; }
     }
+    if (force_rows >= 8 && force_rows <= 10) best = force_rows;
     t.R = best;
     t.tiles_x = (W + TX - 1) / TX;
     t.tiles_y = (H + NW * best - 1) / (NW * best);

@@ -332,7 +332,7 @@ def test_constant_mask_is_fixed_point():
     image = G(synth.image_structured(1, 3, 200, 300, 41))
     mask = torch.full((1, 3, 200, 300), 0.375, device=DEV)
     out = wseg_b200.PAMR(10, D6).to(DEV)(image, mask)
-    assert float((out - 0.375).abs().max()) <= 2e-6
+    assert float((out - 0.375).abs().max()) <= 5e-6  # weights sum to 1 only up to fp32 rounding, 10 iterations
 
 
 def test_multiscale_and_highres_crops_vs_oracle():

@@ -6,12 +6,12 @@ The directory name `1-stage-wseg_b200` is not a Python identifier; import it as 
 from . import _lib
 from .pamr import PAMR, LocalAffinity, LocalAffinityAbs, LocalAffinityCopy, LocalStDev
 from .pamr import local_affinity, propagate, resize_bilinear
-from .stage import (IGNORE_INDEX, labels_from_pseudo_gt, pseudo_gtmask, pseudo_labels, refine_and_label,
+from .stage import (IGNORE_INDEX, HostPipeline, labels_from_pseudo_gt, pseudo_gtmask, pseudo_labels, refine_and_label,
                     rescale_and_clean, run_pamr)
 from .dist import ShardedPseudoLabeler, gather_labels, shard_batch, shard_range
 
 __all__ = [
     "PAMR", "LocalAffinity", "LocalAffinityAbs", "LocalAffinityCopy", "LocalStDev", "local_affinity", "propagate",
     "resize_bilinear", "run_pamr", "rescale_and_clean", "pseudo_gtmask", "pseudo_labels", "labels_from_pseudo_gt",
-    "refine_and_label", "IGNORE_INDEX", "ShardedPseudoLabeler", "gather_labels", "shard_batch", "shard_range",
+    "refine_and_label", "HostPipeline", "IGNORE_INDEX", "ShardedPseudoLabeler", "gather_labels", "shard_batch", "shard_range",
 ]

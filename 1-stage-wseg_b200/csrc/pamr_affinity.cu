@@ -13,6 +13,8 @@
 // denominator use a correctly rounded reciprocal plus one FMA residual correction (Markstein),
 // which returns the IEEE quotient for these operand ranges at a third of the cost of the generic
 // division routine; expf is the accurate libdevice one (no fast-math anywhere).
+#include <atomic>
+
 #include "pamr_common.cuh"
 
 namespace pamr {
@@ -141,6 +143,125 @@ affinity_kernel(const float* __restrict__ img, float* __restrict__ aff, int K, i
     }
 }
 
+// ---- shared-memory staged variant for the standard dilation set [1,2,4,8,12,24] ----
+// A CTA owns a 32 x 8 pixel tile; the K image planes of the tile plus its 24-pixel halo are staged
+// in shared memory once, with replicate padding applied while staging (clamped source
+// coordinates), so every neighbour is a shared-memory load at an immediate offset: no 64-bit
+// address arithmetic, no clamps and ~half the registers of the generic kernel (2 CTAs = 16 warps
+// per SM instead of 8).
+constexpr int SA_BX = 32, SA_BY = 8, SA_HALO = 24;
+constexpr int SA_W = SA_BX + 2 * SA_HALO;  // 80
+constexpr int SA_H = SA_BY + 2 * SA_HALO;  // 56
+constexpr int SA_MAXK = 8;
+__host__ __device__ constexpr int sa_dil(int id) { return id == 0 ? 1 : id == 1 ? 2 : id == 2 ? 4 : id == 3 ? 8 : id == 4 ? 12 : 24; }
+
+template <bool TILED>
+__global__ void __launch_bounds__(SA_BX * SA_BY, 3)
+affinity_smem_kernel(const float* __restrict__ img, float* __restrict__ aff, int K, int H, int W, AffTiling tiling) {
+    extern __shared__ float sa_tile[];  // [K][SA_H][SA_W]
+    const int x0 = blockIdx.x * SA_BX, y0 = blockIdx.y * SA_BY, b = blockIdx.z;
+    const int tid = threadIdx.y * SA_BX + threadIdx.x;
+    const size_t HW = (size_t)H * W;
+    for (int e = tid; e < K * SA_H * SA_W; e += SA_BX * SA_BY) {
+        const int k = e / (SA_H * SA_W), r = e % (SA_H * SA_W), wy = r / SA_W, wx = r % SA_W;
+        const int gy = clampi(y0 - SA_HALO + wy, 0, H - 1), gx = clampi(x0 - SA_HALO + wx, 0, W - 1);
+        sa_tile[e] = __ldg(img + ((size_t)b * K + k) * HW + (size_t)gy * W + gx);
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) {
+        if (TILED && x < tiling.tiles_x * 32 && y < tiling.tiles_y * 4 * tiling.R) {
+            float* __restrict__ out = aff + aff_tiled_index(tiling, b, 0, y, x);
+            const size_t sstride = (size_t)tiling.R * 32;
+#pragma unroll
+            for (int s = 0; s < 48; ++s) out[s * sstride] = 0.f;
+        }
+        return;
+    }
+    float abar[48];
+    for (int k = 0; k < K; ++k) {
+        const float* __restrict__ c0 = sa_tile + (k * SA_H + threadIdx.y + SA_HALO) * SA_W + threadIdx.x + SA_HALO;
+        // the 54 samples are re-read from shared memory in every pass (immediate offsets) rather
+        // than held in registers: 48 accumulators + 54 samples would spill at 128 registers
+#define SA_SMP(i, j) c0[((j) / 3 - 1) * sa_dil(i) * SA_W + ((j) % 3 - 1) * sa_dil(i)]
+        // Unbiased std of the 54 samples in fp32, conditioned so that it tracks torch's double
+        // Welford to ~1e-7 relative: samples are first shifted by the centre value (all rounding
+        // errors then scale with the local contrast, not with the absolute intensity), and both
+        // sums are formed as 6 per-dilation partial sums combined at the end (pairwise-style), so
+        // the accumulation error stays at a few ulp instead of ~54 ulp.  (The FP64 pipe, used by an
+        // earlier version for 810 conversions/adds/FMAs per pixel, was this kernel's bottleneck.)
+        const float cc = c0[0];
+        float su[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) t += SA_SMP(i, j) - cc;
+            su[i] = t;
+        }
+        const float mean_u = (((su[0] + su[1]) + (su[2] + su[3])) + (su[4] + su[5])) * (1.0f / 54.0f);
+        asm volatile("" ::: "memory");  // keep the compiler from caching all 54 samples in registers
+        float sq[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const float dv = (SA_SMP(i, j) - cc) - mean_u;
+                t = fmaf(dv, dv, t);
+            }
+            sq[i] = t;
+        }
+        const float m2 = ((sq[0] + sq[1]) + (sq[2] + sq[3])) + (sq[4] + sq[5]);
+        const float sd = sqrtf(m2 / 53.0f);
+        const float den = __fadd_rn(1e-8f, __fmul_rn(0.1f, sd));
+        const float rden = __frcp_rn(den);
+        asm volatile("" ::: "memory");
+        const float c = c0[0];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int j9 = (j < 4) ? j : j + 1;  // skip the centre sample
+                const float a = div_markstein(-fabsf(__fsub_rn(c, SA_SMP(i, j9))), den, rden);
+                abar[8 * i + j] = (k == 0) ? a : __fadd_rn(abar[8 * i + j], a);
+            }
+        }
+#undef SA_SMP
+    }
+    const float kf = (float)K, rk = __frcp_rn(kf);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int p = 0; p < 48; ++p) {
+        abar[p] = div_markstein(abar[p], kf, rk);
+        mx = fmaxf(mx, abar[p]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < 48; ++p) {
+        abar[p] = expf(abar[p] - mx);
+        s += abar[p];
+    }
+    const float rs = __frcp_rn(s);
+    if (TILED) {
+        float* __restrict__ out = aff + aff_tiled_index(tiling, b, 0, y, x);
+        const size_t sstride = (size_t)tiling.R * 32;
+#pragma unroll
+        for (int p = 0; p < 48; ++p) out[tap_seq(p) * sstride] = div_markstein(abar[p], s, rs);
+    } else {
+        float* __restrict__ out = aff + (size_t)b * 48 * HW + (size_t)y * W + x;
+#pragma unroll
+        for (int p = 0; p < 48; ++p) out[(size_t)p * HW] = div_markstein(abar[p], s, rs);
+    }
+}
+
+bool standard_dilations(const Dilations& dil) {
+    if (dil.nd != 6) return false;
+    for (int i = 0; i < 6; ++i)
+        if (dil.d[i] != sa_dil(i)) return false;
+    return true;
+}
+
 // standard [B,48,H,W] -> tile-major (for callers of the public propagate API)
 __global__ void __launch_bounds__(AFF_BX * AFF_BY)
 aff_relayout_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, AffTiling tiling) {
@@ -161,9 +282,31 @@ aff_relayout_kernel(const float* __restrict__ src, float* __restrict__ dst, int 
 
 int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, const Dilations& dil,
                     const AffTiling& tiling, cudaStream_t s) {
-    dim3 block(AFF_BX, AFF_BY);
     const bool tiled = tiling.R > 0;
     const int gw = tiled ? tiling.tiles_x * 32 : W, gh = tiled ? tiling.tiles_y * 4 * tiling.R : H;
+    if (standard_dilations(dil) && K <= SA_MAXK) {
+        dim3 sblock(SA_BX, SA_BY);
+        dim3 sgrid((gw + SA_BX - 1) / SA_BX, (gh + SA_BY - 1) / SA_BY, B);
+        if (sgrid.y > 65535 || sgrid.z > 65535)
+            return set_error(PAMR_ERR_INVALID_ARGUMENT, "affinity: H/8 and B must be <= 65535");
+        const size_t smem = sizeof(float) * (size_t)K * SA_H * SA_W;
+        static std::atomic<int> attr_set[64];
+        int dev = 0;
+        PAMR_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev >= 64 || attr_set[dev].load(std::memory_order_acquire) == 0) {
+            PAMR_CUDA_TRY(cudaFuncSetAttribute(affinity_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)(sizeof(float) * SA_MAXK * SA_H * SA_W)));
+            PAMR_CUDA_TRY(cudaFuncSetAttribute(affinity_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)(sizeof(float) * SA_MAXK * SA_H * SA_W)));
+            if (dev < 64) attr_set[dev].store(1, std::memory_order_release);
+        }
+        if (tiled) affinity_smem_kernel<true><<<sgrid, sblock, smem, s>>>(img, aff, K, H, W, tiling);
+        else affinity_smem_kernel<false><<<sgrid, sblock, smem, s>>>(img, aff, K, H, W, tiling);
+        count_launch();
+        PAMR_CUDA_TRY(cudaGetLastError());
+        return PAMR_OK;
+    }
+    dim3 block(AFF_BX, AFF_BY);
     dim3 grid((gw + AFF_BX - 1) / AFF_BX, (gh + AFF_BY - 1) / AFF_BY, B);
     if (grid.y > 65535 || grid.z > 65535)
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "affinity: H/4 and B must be <= 65535");

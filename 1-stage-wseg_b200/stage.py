@@ -125,3 +125,59 @@ def refine_and_label(pamr, image_raw, masks, labels, out_size=None, return_masks
     if not return_masks:
         return res
     return (res + (dec,)) if isinstance(res, tuple) else (res, dec)
+
+
+class HostPipeline:
+    """refine_and_label for HOST (pinned) inputs: the batch is cut into chunks and the host->device
+    copy of chunk i+1 overlaps the kernels of chunk i on a second stream; the uint8 label maps are
+    copied back into a pinned host tensor.  This is the call a data-loader-side user makes when
+    image, masks and labels live in host memory (bench.py's `e2e` number).
+
+    Device staging buffers are allocated once per shape and reused across calls."""
+
+    def __init__(self, pamr, device, chunks=4):
+        if not isinstance(pamr, PAMR):
+            raise TypeError("pamr must be a wseg_b200.PAMR module")
+        self.pamr, self.device, self.chunks = pamr, torch.device(device), int(chunks)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._bufs = None
+        self._key = None
+
+    def _buffers(self, image, masks, labels, n):
+        key = (tuple(image.shape[1:]), tuple(masks.shape[1:]), tuple(labels.shape[1:]), n)
+        if self._key != key:
+            mk = lambda t: [torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device) for _ in range(2)]
+            self._bufs = (mk(image), mk(masks), mk(labels))
+            self._key = key
+        return self._bufs
+
+    def __call__(self, h_image, h_masks, h_labels, h_out=None, out_size=None, d_out=None):
+        """Returns the pinned host label map [B,H,W] (uint8), or fills and returns the device tensor
+        d_out instead when one is given (e.g. to all-gather the labels before the copy back)."""
+        B = h_image.shape[0]
+        H, W = _size_of(out_size) if out_size is not None else _size_of(h_image)
+        if h_out is None and d_out is None:
+            h_out = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+        nchunk = max(1, min(self.chunks, B))
+        step = -(-B // nchunk)
+        d_img, d_msk, d_lab = self._buffers(h_image, h_masks, h_labels, step)
+        main = torch.cuda.current_stream(self.device)
+        ready = [torch.cuda.Event() for _ in range(2)]   # chunk copied in
+        freed = [torch.cuda.Event() for _ in range(2)]   # staging buffer consumed
+        spans = [(lo, min(lo + step, B)) for lo in range(0, B, step)]
+        for i, (lo, hi) in enumerate(spans):
+            j, n = i & 1, hi - lo
+            with torch.cuda.stream(self.copy_stream):
+                if i >= 2:
+                    self.copy_stream.wait_event(freed[j])
+                else:
+                    self.copy_stream.wait_stream(main)  # buffers may still be in use by a previous call
+                d_img[j][:n].copy_(h_image[lo:hi], non_blocking=True)
+                d_msk[j][:n].copy_(h_masks[lo:hi], non_blocking=True)
+                d_lab[j][:n].copy_(h_labels[lo:hi], non_blocking=True)
+                ready[j].record(self.copy_stream)
+            main.wait_event(ready[j])
+            lab = refine_and_label(self.pamr, d_img[j][:n], d_msk[j][:n], d_lab[j][:n], (H, W))
+            freed[j].record(main)
+            (d_out if d_out is not None else h_out)[lo:hi].copy_(lab, non_blocking=True)
+        return d_out if d_out is not None else h_out

@@ -1,0 +1,14 @@
+"""Profiling target: the forward path's affinity kernel at config-2 shape."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch, wseg_b200
+D6 = [1, 2, 4, 8, 12, 24]
+dev = "cuda:0"
+B, C, H, W = 16, 21, 321, 321
+image = torch.rand((B, 3, H, W), device=dev); mask = torch.softmax(2 * torch.randn((B, C, H, W), device=dev), 1)
+pamr = wseg_b200.PAMR(1, D6).to(dev)
+for _ in range(3):
+    out = pamr(image, mask)
+torch.cuda.synchronize()
+print("ok", float(out.sum()))

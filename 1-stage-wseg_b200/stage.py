@@ -128,27 +128,37 @@ def refine_and_label(pamr, image_raw, masks, labels, out_size=None, return_masks
 
 
 class HostPipeline:
-    """refine_and_label for HOST (pinned) inputs: the batch is cut into chunks and the host->device
-    copy of chunk i+1 overlaps the kernels of chunk i on a second stream; the uint8 label maps are
-    copied back into a pinned host tensor.  This is the call a data-loader-side user makes when
-    image, masks and labels live in host memory (bench.py's `e2e` number).
+    """refine_and_label for HOST (pinned) inputs, as a data-loader-side caller uses it: inputs are
+    copied host->device on a dedicated copy stream into one of two staging buffer sets, the kernels
+    run on the caller's current stream, and the uint8 label maps are copied back to (pinned) host
+    memory.  The two buffer sets alternate across chunks AND across calls, so the copy of the next
+    batch (or chunk) overlaps the kernels of the current one -- the pattern of a training loop that
+    prefetches its next batch.  The call is asynchronous: synchronise the current stream (or the
+    device) before reading the returned host tensor.  This is bench.py's `e2e` path.
 
-    Device staging buffers are allocated once per shape and reused across calls."""
+    chunks > 1 additionally splits one batch so that its own copy overlaps its own compute (useful
+    for a single large batch; for B=16 at 321x321 the smaller launches cost more than they hide)."""
 
-    def __init__(self, pamr, device, chunks=4):
+    def __init__(self, pamr, device, chunks=1):
         if not isinstance(pamr, PAMR):
             raise TypeError("pamr must be a wseg_b200.PAMR module")
         self.pamr, self.device, self.chunks = pamr, torch.device(device), int(chunks)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self._bufs = None
         self._key = None
+        self._n = 0  # staging buffer sets handed out so far (parity selects the set)
+        self._ready = [torch.cuda.Event() for _ in range(2)]  # set j: inputs copied in
+        self._freed = [torch.cuda.Event() for _ in range(2)]  # set j: consumed by the kernels
 
     def _buffers(self, image, masks, labels, n):
         key = (tuple(image.shape[1:]), tuple(masks.shape[1:]), tuple(labels.shape[1:]), n)
         if self._key != key:
+            torch.cuda.current_stream(self.device).synchronize()  # old buffers may still be in use
+            self.copy_stream.synchronize()
             mk = lambda t: [torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device) for _ in range(2)]
             self._bufs = (mk(image), mk(masks), mk(labels))
             self._key = key
+            self._n = 0
         return self._bufs
 
     def __call__(self, h_image, h_masks, h_labels, h_out=None, out_size=None, d_out=None):
@@ -162,22 +172,19 @@ class HostPipeline:
         step = -(-B // nchunk)
         d_img, d_msk, d_lab = self._buffers(h_image, h_masks, h_labels, step)
         main = torch.cuda.current_stream(self.device)
-        ready = [torch.cuda.Event() for _ in range(2)]   # chunk copied in
-        freed = [torch.cuda.Event() for _ in range(2)]   # staging buffer consumed
-        spans = [(lo, min(lo + step, B)) for lo in range(0, B, step)]
-        for i, (lo, hi) in enumerate(spans):
-            j, n = i & 1, hi - lo
+        for lo in range(0, B, step):
+            hi = min(lo + step, B)
+            j, n = self._n & 1, hi - lo
             with torch.cuda.stream(self.copy_stream):
-                if i >= 2:
-                    self.copy_stream.wait_event(freed[j])
-                else:
-                    self.copy_stream.wait_stream(main)  # buffers may still be in use by a previous call
+                if self._n >= 2:
+                    self.copy_stream.wait_event(self._freed[j])  # set j was last used two chunks ago
                 d_img[j][:n].copy_(h_image[lo:hi], non_blocking=True)
                 d_msk[j][:n].copy_(h_masks[lo:hi], non_blocking=True)
                 d_lab[j][:n].copy_(h_labels[lo:hi], non_blocking=True)
-                ready[j].record(self.copy_stream)
-            main.wait_event(ready[j])
+                self._ready[j].record(self.copy_stream)
+            main.wait_event(self._ready[j])
             lab = refine_and_label(self.pamr, d_img[j][:n], d_msk[j][:n], d_lab[j][:n], (H, W))
-            freed[j].record(main)
+            self._freed[j].record(main)
             (d_out if d_out is not None else h_out)[lo:hi].copy_(lab, non_blocking=True)
+            self._n += 1
         return d_out if d_out is not None else h_out

@@ -252,7 +252,7 @@ def main():
     h_out = torch.empty((world * B if world > 1 else B, H, W), dtype=torch.uint8).pin_memory()
 
     # public host-input API: chunked H2D copies overlapped with the kernels (wseg_b200.HostPipeline)
-    pipe = wseg_b200.HostPipeline(pamr, dev, chunks=int(os.environ.get("PAMR_BENCH_CHUNKS", "2")))
+    pipe = wseg_b200.HostPipeline(pamr, dev, chunks=int(os.environ.get("PAMR_BENCH_CHUNKS", "1")))
     d_local = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
 
     def e2e_step():

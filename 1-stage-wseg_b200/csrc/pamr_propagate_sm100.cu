@@ -143,6 +143,7 @@ struct Params {
     unsigned* cls_max; // [B,C] or nullptr
     int stagger_cta_ns, stagger_grp_ns;  // experiment knobs (env PAMR_B200_STAGGER_CTA / _GRP)
     int dbg_cta;       // CTA that records the timeline
+    int exp_flags;     // experiments (results invalid): 1 skip weight fill, 2 skip global stores, 4 skip halo patch, 8 skip waits
     int pf_class;      // class index at whose TMA issue the next tile's weights are prefetched into L2 (-1: never)
     long long* dbg;    // nullptr, or timeline buffer (debug hook pamr_debug_set_timeline): 2 x 4096 x {clock, code}
     int dst_pitch;
@@ -491,7 +492,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 // parallelism is what bounds this phase (the accumulators are not live here)
                 constexpr int TAPS_PER_GROUP = 48 / NG, FILL_TAPS = 8;
 #pragma unroll
-                for (int h = 0; h < TAPS_PER_GROUP / FILL_TAPS; ++h) {
+                for (int h = 0; h < ((prm.exp_flags & 1) ? 0 : TAPS_PER_GROUP / FILL_TAPS); ++h) {
                     const int s0 = TAPS_PER_GROUP * grp + h * FILL_TAPS;  // grp is warp-uniform; offsets below are immediates
                     const float* __restrict__ bp = ap + (size_t)s0 * R * 32;
                     float r[FILL_TAPS][R];
@@ -521,8 +522,8 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 const int s = (int)(sq % NSLOT);
                 const uint32_t par = (uint32_t)(sq / NSLOT) & 1u;
                 PAMR_EV(100 + k);
-                if (!probe) mbar_wait(smem_u32(&ctrl->tma_bar[s]), par);  // bytes landed
-                if (border) {  // replicate padding: the group patches the halo of its own slot
+                if (!probe && !(prm.exp_flags & 8)) mbar_wait(smem_u32(&ctrl->tma_bar[s]), par);  // bytes landed
+                if (border && !(prm.exp_flags & 4)) {  // replicate padding: the group patches the halo of its own slot
                     patch_window<R>(slots + (size_t)s * C_::SLOT_FLOATS, x0, y0, H, W, wq, lane);
                     asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(NW * 32) : "memory");
                 }
@@ -560,7 +561,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                         unsigned mx = 0u;
 #pragma unroll
                         for (int i = 0; i < R; ++i) {
-                            if (xok && yw + i < H) {
+                            if (xok && yw + i < H && !(prm.exp_flags & 2)) {
                                 op[(size_t)i * prm.dst_pitch] = acc[j][i];
                                 mx = max(mx, ordered_from_float(acc[j][i]));
                             }
@@ -651,6 +652,7 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
     static const int knob_pf = getenv("PAMR_B200_PF_CLASS") ? atoi(getenv("PAMR_B200_PF_CLASS")) : -2;
     p.pf_class = (knob_pf == -2) ? (C >= 3 ? C - 3 : 0) : (knob_pf < C ? knob_pf : -1);
     p.dbg_cta = getenv("PAMR_B200_DBG_CTA") ? atoi(getenv("PAMR_B200_DBG_CTA")) : 0;
+    p.exp_flags = getenv("PAMR_B200_EXPERIMENT") ? atoi(getenv("PAMR_B200_EXPERIMENT")) : 0;
     p.B = B; p.C = C; p.H = H; p.W = W;
     p.tiles_x = (Wt + TX - 1) / TX;
     p.tiles_y = tiling.tiles_y;

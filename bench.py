@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -66,10 +66,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi takes a moment to attach; do not let its start-up overlap the timed region."""
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.rows and time.time() < t_end:
+            time.sleep(0.02)
+
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 7] or \
                [r for (_, r) in self.rows if len(r) >= 7]
@@ -140,7 +146,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
@@ -217,8 +223,12 @@ def main():
     sampler = ClockSampler(dev.index)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
+    for _ in range(args.warmup):  # untimed warm-up (clocks ramp, allocator pools fill) before the clock window opens
+        step(image, mask, labels)
+    barrier()
     t_wall0 = time.time()
-    ms_step, launches = timed(lambda: step(image, mask, labels), args.steps, args.warmup)
+    ms_step, launches = timed(lambda: step(image, mask, labels), args.steps, 0)
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     if args.only == "step":

@@ -6,17 +6,18 @@
 //
 // This file holds the iteration driver, the GENERIC kernel (any dilation list, any C, any H/W:
 // one thread per pixel, neighbours fetched through L1 with clamped coordinates) and the STRIP
-// kernel that covers the few right-most columns the tuned kernel leaves out.  The tuned sm_100a
+// (the few remainder columns / rows the tuned kernel's tiles leave out are computed inside the tuned launch).  The tuned sm_100a
 // kernel for the standard dilation set lives in pamr_propagate_sm100.cu.
 #include "pamr_common.cuh"
 
 namespace pamr {
 
 // pamr_propagate_sm100.cu
-int tuned_width(int W);
 int launch_repack(const float* src, float* dst, int planes, int H, int W, int Wp, cudaStream_t s);
+bool tuned_has_strips(int H, int W, const AffTiling& tiling);
 int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, int src_pitch, float* dst,
-                           int dst_pitch, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s);
+                           int dst_pitch, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s,
+                           cudaStream_t side);
 
 namespace {
 
@@ -70,46 +71,6 @@ propagate_generic_kernel(const float* __restrict__ aff, const float* __restrict_
     }
 }
 
-// Remainder strip x in [x_begin, W) next to the tuned kernel's tiles (standard dilations, tiled
-// affinity).  One thread per (pixel, class): the strip is a few thousand pixels, so parallelism
-// over classes is what keeps this launch in the microsecond range.
-__global__ void __launch_bounds__(256)
-propagate_strip_kernel(const float* __restrict__ aff, AffTiling tiling, const float* __restrict__ m_in, int src_pitch,
-                       float* __restrict__ m_out, int dst_pitch, int B, int C, int H, int W, int x_begin,
-                       unsigned* __restrict__ cls_max) {
-    const int xw = W - x_begin;
-    const long long total = (long long)B * C * H * xw;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;  // (only whole tail warps or a tail of lanes exit: __activemask below covers it)
-    const int x = x_begin + (int)(t % xw);
-    const int y = (int)((t / xw) % H);
-    const int c = (int)((t / ((long long)xw * H)) % C);
-    const int b = (int)(t / ((long long)xw * H * C));
-    const float* __restrict__ pl = m_in + ((size_t)b * C + c) * H * src_pitch;
-    const float* __restrict__ wp = aff + aff_tiled_index(tiling, b, 0, y, x);
-    const size_t sstride = (size_t)tiling.R * 32;
-    const int dils[6] = {1, 2, 4, 8, 12, 24};
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const int d = dils[i];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int yy = clampi(y + tap_dy(j) * d, 0, H - 1);
-            const int xx = clampi(x + tap_dx(j) * d, 0, W - 1);
-            acc = fmaf(__ldg(wp + tap_seq(8 * i + j) * sstride), __ldg(pl + (size_t)yy * src_pitch + xx), acc);
-        }
-    }
-    m_out[(((size_t)b * C + c) * H + y) * dst_pitch + x] = acc;
-    if (cls_max != nullptr) {
-        // one atomic per (warp, plane): neighbouring lanes are neighbouring pixels of the same plane
-        const unsigned key = (unsigned)(b * C + c);
-        const unsigned peers = __match_any_sync(__activemask(), key);
-        const unsigned m = __reduce_max_sync(peers, ordered_from_float(acc));
-        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicMax(cls_max + key, m);
-    }
-}
-
 __global__ void class_max_kernel(const float* __restrict__ m, unsigned* __restrict__ cls_max, size_t HW) {
     // used only when iters == 0 and a max is requested
     const size_t plane = blockIdx.y;
@@ -135,18 +96,6 @@ int launch_generic(const float* aff, const float* src, int src_pitch, float* dst
     if (grid.y > 65535 || grid.z > 65535)
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: H/8 and B must be <= 65535");
     propagate_generic_kernel<<<grid, block, 0, s>>>(aff, src, src_pitch, dst, dst_pitch, C, H, W, dil, cls_max);
-    count_launch();
-    PAMR_CUDA_TRY(cudaGetLastError());
-    return PAMR_OK;
-}
-
-int launch_strip(const float* aff_tiled, const AffTiling& tiling, const float* src, int src_pitch, float* dst,
-                 int dst_pitch, int B, int C, int H, int W, int x_begin, unsigned* cls_max, cudaStream_t s) {
-    const long long total = (long long)B * C * H * (W - x_begin);
-    const long long blocks = (total + 255) / 256;
-    if (blocks > 0x7fffffffLL) return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: strip too large");
-    propagate_strip_kernel<<<(unsigned)blocks, 256, 0, s>>>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W,
-                                                           x_begin, cls_max);
     count_launch();
     PAMR_CUDA_TRY(cudaGetLastError());
     return PAMR_OK;
@@ -251,12 +200,10 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
     float* P[2] = {(float*)scratch, (float*)((char*)scratch + plan.pingpong_each)};
     if (!tuned && aff_is_tiled)
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: tiled affinity without the tuned kernel");
-    const int Wt = tuned ? tuned_width(W) : 0;
     const bool need_repack = tuned && ((W & 3) != 0 || ((uintptr_t)m_in & 15) != 0);
-    const bool need_strip = tuned && Wt < W;
 
     ForkJoin fj;
-    if (need_repack || need_strip) {
+    if (need_repack) {
         int rc = fj.init(dev, s);
         if (rc != PAMR_OK) return rc;
     }
@@ -288,13 +235,8 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
         const int dst_pitch = last ? W : Wp;
         unsigned* mx = last ? cls_max : nullptr;
         if (tuned) {
-            if (need_strip) {  // remainder columns on the side stream, concurrently with the tiles
-                if ((rc = fj.fork()) != PAMR_OK) return rc;
-                rc = launch_strip(aff, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, mx, fj.side);
-                if (rc != PAMR_OK) return rc;
-            }
-            rc = launch_propagate_tuned(aff, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, mx, dev, s);
-            if (rc == PAMR_OK && need_strip) rc = fj.join();
+            // (remainder columns / rows are computed inside the same launch, at tile boundaries)
+            rc = launch_propagate_tuned(aff, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, mx, dev, s, nullptr);
         } else {
             rc = launch_generic(aff, src, src_pitch, dst, dst_pitch, B, C, H, W, dil, mx, s);
         }

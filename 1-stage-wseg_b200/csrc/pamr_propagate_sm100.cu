@@ -149,7 +149,11 @@ struct Params {
     int dst_pitch;
     int B, C, H, W;
     int tiles_x, tiles_y, ntiles;  // tiles of this launch (tiles_x may exclude the remainder strip)
-    int tiles_x_aff;               // tile columns of the affinity layout
+    int tiles_x_aff, tiles_y_aff;  // tile grid of the affinity layout (covers the whole image)
+    const float* src;              // source mask [B,C,H,src_pitch] (for the remainder strips; tiles come through TMA)
+    int src_pitch;
+    int Wt, Ht;                    // the tiles cover [0,Wt) x [0,Ht); the producer warp computes the remainder strips
+    int strip_items;               // number of 32-pixel strip work items (all CTAs together)
 };
 
 // ---------------------------------------------------------------- TMEM weight layout
@@ -389,6 +393,52 @@ __device__ __forceinline__ void compute_bar_sync() {  // the NWC compute warps o
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+// Remainder strips.  The tiles cover [0,Wt) x [0,Ht); when W or H leaves a remainder of at most 8
+// pixels (W = H = 321 -> one column and one row) that remainder is not worth a tile row/column of
+// its own.  It is cut into work items of 32 pixels -- item < n_col: 32 rows of one strip column,
+// otherwise 32 columns of one strip row -- which the compute warps pick up at tile boundaries
+// (one pixel per lane, neighbours and weights straight from global memory / L2, clamped coordinates).
+template <int R>
+__device__ __forceinline__ void strip_item(const Params& prm, int item, int lane) {
+    const int C = prm.C, H = prm.H, W = prm.W;
+    const int wcols = W - prm.Wt, hrows = H - prm.Ht;
+    const int yblocks = (H + 31) / 32, xblocks = (prm.Wt + 31) / 32;
+    const int per_plane = wcols * yblocks + hrows * xblocks;
+    const int plane = item / per_plane, r = item % per_plane;  // plane = b*C + c
+    int x, y;
+    if (r < wcols * yblocks) {
+        x = prm.Wt + r / yblocks;
+        y = (r % yblocks) * 32 + lane;
+    } else {
+        const int q = r - wcols * yblocks;
+        y = prm.Ht + q / xblocks;
+        x = (q % xblocks) * 32 + lane;
+        if (x >= prm.Wt) x = W;  // beyond the row strip (those columns belong to the column strip)
+    }
+    const bool valid = (y < H) && (x < W);
+    const int yc = min(y, H - 1), xc = min(x, W - 1);
+    const int b = plane / C;
+    const float* __restrict__ pl = prm.src + (size_t)plane * H * prm.src_pitch;
+    const AffTiling tl{R, prm.tiles_x_aff, prm.tiles_y_aff};
+    const float* __restrict__ wp = prm.aff + aff_tiled_index(tl, b, 0, yc, xc);
+    float acc = 0.f;
+#pragma unroll
+    for (int id = 0; id < 6; ++id) {
+        const int d = dil_of(id);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int yy = clampi(yc + tap_dy(j) * d, 0, H - 1);
+            const int xx = clampi(xc + tap_dx(j) * d, 0, W - 1);
+            acc = fmaf(__ldg(wp + tap_seq(8 * id + j) * (R * 32)), __ldg(pl + (size_t)yy * prm.src_pitch + xx), acc);
+        }
+    }
+    if (valid) prm.dst[((size_t)plane * H + y) * prm.dst_pitch + x] = acc;
+    if (prm.cls_max != nullptr) {
+        const unsigned m = __reduce_max_sync(0xffffffffu, valid ? ordered_from_float(acc) : 0u);
+        if (lane == 0 && m != 0u) atomicMax(prm.cls_max + plane, m);
+    }
+}
+
 template <int R>
 __global__ void __launch_bounds__(NTHREADS, 1)
 propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params prm) {
@@ -431,8 +481,8 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
             const int x0 = (t % prm.tiles_x) * TX, y0 = (t / prm.tiles_x) * C_::TY;
+            if (lane == 0) mbar_wait(smem_u32(&ctrl->empty_bar[s]), (round & 1u) ^ 1u);
             if (lane == 0) {
-                mbar_wait(smem_u32(&ctrl->empty_bar[s]), (round & 1u) ^ 1u);
                 const uint32_t bar = smem_u32(&ctrl->tma_bar[s]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive_expect_tx(bar, C_::SLOT_BYTES);
@@ -449,7 +499,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             if (c == prm.pf_class && ti + 1 < my_tiles && lane < 4) {
                 const int ntile = (int)blockIdx.x + (ti + 1) * (int)gridDim.x;
                 const int nb = ntile / tiles_per_img, nt = ntile % tiles_per_img;
-                const float* wp = prm.aff + (((((size_t)nb * prm.tiles_y + nt / prm.tiles_x) * prm.tiles_x_aff +
+                const float* wp = prm.aff + (((((size_t)nb * prm.tiles_y_aff + nt / prm.tiles_x) * prm.tiles_x_aff +
                                                nt % prm.tiles_x) * 4 + lane) * 48 * R) * 32;
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wp), "r"(48 * R * 32 * 4) : "memory");
             }
@@ -487,7 +537,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 // tile-major layout: this thread's weights are ap[(s*R + i)*32], s = tap sequence index
                 const int ty = t / prm.tiles_x, tx = t % prm.tiles_x;
                 const float* __restrict__ ap =
-                    prm.aff + (((((size_t)b * prm.tiles_y + ty) * prm.tiles_x_aff + tx) * 4 + wq) * 48 * R) * 32 + lane;
+                    prm.aff + (((((size_t)b * prm.tiles_y_aff + ty) * prm.tiles_x_aff + tx) * 4 + wq) * 48 * R) * 32 + lane;
                 // FILL_TAPS*R loads are in flight before the first TMEM store: memory-level
                 // parallelism is what bounds this phase (the accumulators are not live here)
                 constexpr int TAPS_PER_GROUP = 48 / NG, FILL_TAPS = 8;
@@ -583,6 +633,84 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(ctrl->tmem_base), "r"(512));
 }
 
+// ---- remainder strips as two small launches in front of the persistent kernel ----
+// (Alternatives measured on B200 and rejected: the same work inside the persistent kernel -- by the
+//  producer warp its ~100 global loads per item queue behind the compute warps' LDS traffic, by
+//  the compute warps at tile boundaries it lengthens every boundary; a concurrent side-stream
+//  launch does not co-reside with the persistent CTAs; partial tiles cost a whole tile column.)
+
+// Row strip: y in [Ht,H), all x.  One warp per 32 consecutive pixels of a row (coalesced).
+template <int R>
+__global__ void __launch_bounds__(128) strip_rows_kernel(const Params prm) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < prm.strip_items; item += gridDim.x * wpb)
+        strip_item<R>(prm, item, lane);
+}
+
+// Column strip: x in [Wt,W), all y.  Neighbours of a column of pixels lie in different rows, i.e.
+// in different cache lines, so one CTA stages the last 24 + (W-Wt) columns of 32 + 48 rows of all C
+// class planes in shared memory with coalesced row reads (one warp per class plane), then every
+// warp computes 32 pixels (lane = row) x (W-Wt) columns of its class from shared memory.
+constexpr int SC_ROWS = 32;                      // pixel rows per CTA
+constexpr int SC_WIN_H = SC_ROWS + 2 * HALO;     // 80
+constexpr int SC_WIN_W = 32;                     // staged columns [W-32, W)  (needs W >= 32)
+constexpr int SC_CG = 16;                        // class planes staged at a time (one warp each)
+template <int R>
+__global__ void __launch_bounds__(SC_CG * 32) strip_cols_kernel(const Params prm) {
+    extern __shared__ float sc_smem[];  // [SC_CG][SC_WIN_H][SC_WIN_W + 1] then weights [wc][48][32]
+    const int C = prm.C, H = prm.H, W = prm.W, wc = W - prm.Wt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int yb = blockIdx.x * SC_ROWS, b = blockIdx.y;
+    constexpr int PITCH = SC_WIN_W + 1;
+    float* wsm = sc_smem + (size_t)SC_CG * SC_WIN_H * PITCH;
+    const int xs0 = W - SC_WIN_W;  // first staged column
+    // the weights of the strip pixels: wsm[(xi*48 + s)*32 + row]
+    const AffTiling tl{R, prm.tiles_x_aff, prm.tiles_y_aff};
+    for (int e = threadIdx.x; e < wc * 48 * SC_ROWS; e += blockDim.x) {
+        const int row = e % SC_ROWS, s = (e / SC_ROWS) % 48, xi = e / (SC_ROWS * 48);
+        wsm[e] = __ldg(prm.aff + aff_tiled_index(tl, b, s, min(yb + row, H - 1), prm.Wt + xi));
+    }
+    const int y = yb + lane;
+    float* mywin = sc_smem + (size_t)warp * SC_WIN_H * PITCH;
+    for (int c0 = 0; c0 < C; c0 += SC_CG) {
+        const int c = c0 + warp;
+        if (c < C) {  // stage this warp's class plane window (rows clamped: replicate padding)
+            const float* __restrict__ pl = prm.src + ((size_t)b * C + c) * H * prm.src_pitch;
+            // all 80 row loads in flight at once (latency-, not bandwidth-bound)
+            float v[SC_WIN_H];
+#pragma unroll
+            for (int r = 0; r < SC_WIN_H; ++r)
+                v[r] = __ldg(pl + (size_t)clampi(yb - HALO + r, 0, H - 1) * prm.src_pitch + xs0 + lane);
+#pragma unroll
+            for (int r = 0; r < SC_WIN_H; ++r) mywin[r * PITCH + lane] = v[r];
+        }
+        __syncthreads();  // also covers the weights on the first round
+        if (c < C) {
+            const float* win = mywin + (lane + HALO) * PITCH;
+            for (int xi = 0; xi < wc; ++xi) {
+                const int xl = prm.Wt + xi - xs0;  // column inside the staged window
+                float acc = 0.f;
+#pragma unroll
+                for (int id = 0; id < 6; ++id) {
+                    const int d = dil_of(id);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int xx = min(xl + tap_dx(j) * d, SC_WIN_W - 1);  // clamp at the right image border
+                        acc = fmaf(wsm[(xi * 48 + tap_seq(8 * id + j)) * SC_ROWS + lane], win[tap_dy(j) * d * PITCH + xx], acc);
+                    }
+                }
+                const bool valid = y < H;
+                if (valid) prm.dst[(((size_t)b * C + c) * H + y) * prm.dst_pitch + prm.Wt + xi] = acc;
+                if (prm.cls_max != nullptr) {
+                    const unsigned m = __reduce_max_sync(0xffffffffu, valid ? ordered_from_float(acc) : 0u);
+                    if (lane == 0 && m != 0u) atomicMax(prm.cls_max + (size_t)b * C + c, m);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Copy [planes,H,W] -> [planes,H,Wp] (Wp % 4 == 0) so that TMA's 16-byte stride rule holds.
 __global__ void repack_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int Wp, size_t rows) {
     for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -628,7 +756,8 @@ int make_tmap(CUtensorMap* map, const float* base, int planes, int H, int W, int
 
 template <int R>
 int launch_one(const float* aff, const AffTiling& tiling, const float* src, int src_pitch, float* dst, int dst_pitch,
-               int B, int C, int H, int W, int Wt, unsigned* cls_max, int sm_count, cudaStream_t s) {
+               int B, int C, int H, int W, int Wt, int Ht, unsigned* cls_max, int sm_count, cudaStream_t s,
+               cudaStream_t side) {
     using C_ = Cfg<R>;
     // function attributes are per device: set once per (kernel, device)
     static std::atomic<int> attr_set[64];
@@ -655,11 +784,40 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
     p.exp_flags = getenv("PAMR_B200_EXPERIMENT") ? atoi(getenv("PAMR_B200_EXPERIMENT")) : 0;
     p.B = B; p.C = C; p.H = H; p.W = W;
     p.tiles_x = (Wt + TX - 1) / TX;
-    p.tiles_y = tiling.tiles_y;
+    p.tiles_y = (Ht + C_::TY - 1) / C_::TY;
     p.tiles_x_aff = tiling.tiles_x;
+    p.tiles_y_aff = tiling.tiles_y;
+    p.src = src; p.src_pitch = src_pitch; p.Wt = Wt; p.Ht = Ht;
+    p.strip_items = 0;
+    const bool skip_strips = getenv("PAMR_B200_EXPERIMENT") && (atoi(getenv("PAMR_B200_EXPERIMENT")) & 16);
+    if (Ht < H && !skip_strips) {  // row strip y in [Ht,H), all columns
+        Params pr = p;
+        pr.Wt = W;  // strip_item: no column part, the row part spans [0,W)
+        const long long items = (long long)B * C * (H - Ht) * ((W + 31) / 32);
+        if (items > 0x7fffffffLL) return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: row strip too large");
+        pr.strip_items = (int)items;
+        const int blocks = (int)((items + 3) / 4);
+        strip_rows_kernel<R><<<blocks < 8 * sm_count ? blocks : 8 * sm_count, 128, 0, s>>>(pr);
+        count_launch();
+        PAMR_CUDA_TRY(cudaGetLastError());
+    }
+    if (Wt < W && !skip_strips) {  // column strip x in [Wt,W), all rows
+        const size_t smem = sizeof(float) * ((size_t)SC_CG * SC_WIN_H * (SC_WIN_W + 1) + (size_t)(W - Wt) * 48 * SC_ROWS);
+        static std::atomic<int> sc_attr[64];
+        if (dev >= 64 || sc_attr[dev].load(std::memory_order_acquire) == 0) {
+            PAMR_CUDA_TRY(cudaFuncSetAttribute(strip_cols_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            if (dev < 64) sc_attr[dev].store(1, std::memory_order_release);
+        }
+        dim3 grid((H + SC_ROWS - 1) / SC_ROWS, B);
+        strip_cols_kernel<R><<<grid, SC_CG * 32, smem, s>>>(p);
+        count_launch();
+        PAMR_CUDA_TRY(cudaGetLastError());
+    }
     p.ntiles = p.tiles_x * p.tiles_y * B;
     const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
-    propagate_sm100_kernel<R><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, p);
+    Params pm = p;
+    (void)side;
+    propagate_sm100_kernel<R><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, pm);
     count_launch();
     PAMR_CUDA_TRY(cudaGetLastError());
     return PAMR_OK;
@@ -671,11 +829,20 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
 // subsequent tuned launch fills with {clock64, event code} pairs; nullptr switches it off.
 extern "C" void pamr_debug_set_timeline(long long* dev_buf) { g_timeline.store(dev_buf); }
 
-// Width handled by the tuned kernel; a short remainder strip [Wt, W) goes to the strip kernel
-// so that a tile column with only a few live lanes is not paid for (W = 321 -> 10 tile columns + 1 px).
+// Extent handled by the tuned kernel's tiles; a remainder of at most 8 columns / rows goes to the
+// in-kernel strips (producer warp), so that a tile column / row with only a few live pixels is not
+// paid for (W = H = 321 -> 10 x 8 tiles of 32 x 40 plus one column and one row).
+static int strip_max() {  // largest remainder (pixels) handled as a strip; PAMR_B200_STRIP_MAX overrides
+    static const int v = getenv("PAMR_B200_STRIP_MAX") ? atoi(getenv("PAMR_B200_STRIP_MAX")) : 8;
+    return v;
+}
 int tuned_width(int W) {
     const int rem = W % TX;
-    return (rem != 0 && rem <= 8) ? W - rem : W;
+    return (rem != 0 && rem <= strip_max() && W > TX) ? W - rem : W;
+}
+int tuned_height(int H, int R) {
+    const int ty = NW * R, rem = H % ty;
+    return (rem != 0 && rem <= strip_max() && H > ty) ? H - rem : H;
 }
 
 // Tiling of the tuned kernel (R rows per thread, tile = 32 x 4R) or R == 0 when it does not apply.
@@ -697,8 +864,8 @@ AffTiling tuned_tiling(int H, int W, const Dilations& dil) {
     int best = 10;
     double best_cost = 1e30;
     for (int r = 8; r <= 10; ++r) {
-        const int ty = NW * r;
-        const double cost = (double)((H + ty - 1) / ty * ty) * (r == 10 ? 1.11 : r == 9 ? 1.13 : 1.19);
+        const int ty = NW * r, ht = tuned_height(H, r);
+        const double cost = (double)((ht + ty - 1) / ty * ty) * (r == 10 ? 1.11 : r == 9 ? 1.13 : 1.19);
         if (cost < best_cost) { best = r; best_cost = cost; }
     }
     if (force_rows >= 8 && force_rows <= 10) best = force_rows;
@@ -719,8 +886,15 @@ int launch_repack(const float* src, float* dst, int planes, int H, int W, int Wp
 
 // One propagation step src -> dst with the tuned kernel over x in [0, tuned_width(W)).
 // src must have a pitch that is a multiple of 4 floats and a 16-byte aligned base.
+bool tuned_has_strips(int H, int W, const AffTiling& tiling) {
+    return tuned_width(W) < W || tuned_height(H, tiling.R) < H;
+}
+
+// `side`: stream (already ordered after the producer of `src`) for the remainder-strip launch, or
+// nullptr to let the persistent kernel's producer warp compute the strips itself.
 int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, int src_pitch, float* dst,
-                           int dst_pitch, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s) {
+                           int dst_pitch, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s,
+                           cudaStream_t side) {
     static int sm_counts[64] = {0};
     int sm_count = (dev >= 0 && dev < 64) ? sm_counts[dev] : 0;
     if (sm_count == 0) {
@@ -729,10 +903,10 @@ int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, cons
     }
     if ((src_pitch & 3) != 0 || ((uintptr_t)src & 15) != 0)
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: source pitch/base not 16-byte aligned");
-    const int Wt = tuned_width(W);
-    if (tiling.R == 8) return launch_one<8>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, cls_max, sm_count, s);
-    if (tiling.R == 9) return launch_one<9>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, cls_max, sm_count, s);
-    return launch_one<10>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, cls_max, sm_count, s);
+    const int Wt = tuned_width(W), Ht = tuned_height(H, tiling.R);
+    if (tiling.R == 8) return launch_one<8>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, side);
+    if (tiling.R == 9) return launch_one<9>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, side);
+    return launch_one<10>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, side);
 }
 
 }  // namespace pamr

@@ -160,12 +160,29 @@ __global__ void __launch_bounds__(SA_BX * SA_BY, 3)
 affinity_smem_kernel(const float* __restrict__ img, float* __restrict__ aff, int K, int H, int W, AffTiling tiling) {
     extern __shared__ float sa_tile[];  // [K][SA_H][SA_W]
     const int x0 = blockIdx.x * SA_BX, y0 = blockIdx.y * SA_BY, b = blockIdx.z;
-    const int tid = threadIdx.y * SA_BX + threadIdx.x;
     const size_t HW = (size_t)H * W;
-    for (int e = tid; e < K * SA_H * SA_W; e += SA_BX * SA_BY) {
-        const int k = e / (SA_H * SA_W), r = e % (SA_H * SA_W), wy = r / SA_W, wx = r % SA_W;
-        const int gy = clampi(y0 - SA_HALO + wy, 0, H - 1), gx = clampi(x0 - SA_HALO + wx, 0, W - 1);
-        sa_tile[e] = __ldg(img + ((size_t)b * K + k) * HW + (size_t)gy * W + gx);
+    // staging: thread (tx,ty) covers window columns tx, tx+32, tx+64 and rows ty, ty+8, ... of every
+    // plane; all 21 loads of a plane are in flight before the first shared-memory store
+    for (int k = 0; k < K; ++k) {
+        const float* __restrict__ pl = img + ((size_t)b * K + k) * HW;
+        float v[3][SA_H / SA_BY];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+            const int wx = threadIdx.x + 32 * cc;
+            const int gx = clampi(x0 - SA_HALO + wx, 0, W - 1);
+#pragma unroll
+            for (int rr = 0; rr < SA_H / SA_BY; ++rr) {
+                const int gy = clampi(y0 - SA_HALO + (int)threadIdx.y + SA_BY * rr, 0, H - 1);
+                v[cc][rr] = (wx < SA_W) ? __ldg(pl + (size_t)gy * W + gx) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+            const int wx = threadIdx.x + 32 * cc;
+#pragma unroll
+            for (int rr = 0; rr < SA_H / SA_BY; ++rr)
+                if (wx < SA_W) sa_tile[(k * SA_H + threadIdx.y + SA_BY * rr) * SA_W + wx] = v[cc][rr];
+        }
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;

@@ -3,22 +3,25 @@
 //
 //   M'[b,c,y,x] = sum_{p<48} w[b,p,y,x] * M[b,c,clamp(y+dy_p),clamp(x+dx_p)]
 //
-// Design (DESIGN.md "propagate_sm100"):
+// Design:
 //  * persistent CTAs, one per SM; a CTA owns a 32 x (4*R) pixel tile (R = 8, 9 or 10 rows per thread);
-//  * 4 compute warps: lane = x, each thread owns a vertical strip of R pixels, so that one
-//    shared-memory load feeds up to 3*R/(R+2d) taps (register reuse along y): ~32 LDS per
-//    pixel-class instead of 48;
-//  * the tile's 48 affinity weights per pixel (48*R words per thread) are read from HBM ONCE per
-//    tile and parked in Tensor Memory (tcgen05.st), 1 TMEM lane per thread; every class group
-//    re-reads them with tcgen05.ld -- a data path that does not compete with LDS -- instead of
-//    holding them in registers or re-reading them through L1;
-//  * a producer warp streams the 21 class planes of the tile (+24 px halo, 80 x (4R+48) floats)
+//  * 12 compute warps in 3 groups of 4: lane = x, each thread owns a vertical strip of R pixels, so
+//    that one shared-memory load feeds up to 3*R/(R+2d) taps (register reuse along y): ~32 LDS per
+//    pixel-class instead of 48.  Group g takes the class planes c = g (mod 3);
+//  * the tile's 48 affinity weights per pixel (48*R words per thread) are read once per tile and
+//    parked in Tensor Memory (tcgen05.st), 1 TMEM lane per thread, shared by the three groups (warps
+//    w, w+4, w+8 address the same lane quarter); every class pass re-reads them with tcgen05.ld -- a
+//    data path that does not compete with LDS -- instead of holding them in registers or
+//    re-reading them through L1.  The next tile's weights are pulled into L2 with a bulk prefetch
+//    three classes before the tile boundary;
+//  * a producer warp streams the class planes of the tile (+24 px halo, 80 x (4R+48) floats)
 //    through an 8-slot shared-memory ring with TMA (cp.async.bulk.tensor.3d) + mbarriers; TMA
-//    zero-fills outside the image, so for border tiles the producer warp patches the halo in
-//    shared memory to replicate padding (pamr.py:50) before releasing the slot;
-//  * compute warps take 3 class planes at a time (27-30 accumulators), FP32 FMA, and store the
-//    result with coalesced 128-byte rows; the per-(b,c) max for pseudo_gtmask is fused into the
-//    last iteration (warp reduce + atomicMax).
+//    zero-fills outside the image, so for border tiles the consuming group patches the halo in
+//    shared memory to replicate padding (pamr.py:50) before it computes;
+//  * FP32 math as packed FFMA2 over adjacent rows (a scalar FFMA with three distinct source
+//    registers issues only every ~1.8 cycles); results are stored with coalesced 128-byte rows; the
+//    per-(b,c) max for pseudo_gtmask is fused into the last iteration (warp reduce + atomicMax);
+//  * remainders of at most 8 columns / rows (W = H = 321) are computed by two small strip kernels.
 #include <cuda.h>
 
 #include <atomic>
@@ -93,12 +96,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-        ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]), "f"(r[8]),
-        "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]));
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
 #ifdef PAMR_BODY_NO_TMEM
     for (int j = 0; j < 16; ++j) r[j] = __uint_as_float(taddr + j) * 1e-30f;
@@ -506,8 +503,8 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             __syncwarp();
         }
     } else {
-        // ===================== compute warps: 2 groups x NW warps =====================
-        const int grp = warp / NW, wq = warp % NW;  // wq = TMEM lane quarter; both groups share the weights
+        // ===================== compute warps: NG groups x NW warps =====================
+        const int grp = warp / NW, wq = warp % NW;  // wq = TMEM lane quarter; all groups share the weights
         const uint32_t tbase = ctrl->tmem_base + ((uint32_t)(wq * 32) << 16);
         int dn = 0;  // timeline events written by this group's leader lane of CTA 0
         if ((blockIdx.x & 1) && prm.stagger_cta_ns > 0) __nanosleep(prm.stagger_cta_ns);
@@ -529,7 +526,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             const bool border = needs_patch<R>(x0, y0, H, W);
 
             // ---- park the tile's 48*R weights per thread in TMEM (layout: TmemLayout); each group
-            //      loads half of the taps for the lanes it shares with its sibling warp
+            //      loads its share (48/NG) of the taps for the lanes it shares with its sibling warps
             PAMR_EV(1);
             if (ti > 0) compute_bar_sync();  // nobody still reads the previous tile's weights
             PAMR_EV(2);

@@ -144,6 +144,19 @@ def test_pamr_vs_oracle_edge_shapes(hw):
     assert np.abs(out - ref).max() <= TOL
 
 
+@pytest.mark.parametrize("hw", [(41, 64), (72, 33), (45, 71), (88, 40), (83, 97), (321, 33)])
+def test_pamr_vs_oracle_remainder_strips(hw):
+    """Shapes whose remainders (<= 8 rows / columns past the last full tile) go to the strip kernels."""
+    H, W = hw
+    image, mask = synth.image_structured(2, 3, H, W, 15), synth.mask_softmax(2, 21, H, W, 16)
+    ref = oracle.pamr_forward(image, mask, 10, D6)
+    out, cmax = wseg_b200.PAMR(10, D6).to(DEV)(G(image), G(mask), return_class_max=True)
+    assert np.abs(N(out) - ref).max() <= TOL
+    L = _lib.lib()
+    got = np.array([[L.pamr_float_from_ordered(int(v) & 0xffffffff) for v in row] for row in N(cmax)], dtype=np.float32)
+    np.testing.assert_array_equal(got, N(out.flatten(2).max(-1).values))
+
+
 @pytest.mark.parametrize("C", [1, 2, 7, 8, 20, 22, 40])
 def test_pamr_vs_oracle_class_counts(C):
     image, mask = synth.image_uniform(1, 3, 50, 70, 7), synth.mask_softmax(1, C, 50, 70, 8)

@@ -230,8 +230,12 @@ __device__ __forceinline__ void fma2(float& a0, float& a1, float w0, float w1, f
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(A));
 }
 
+// xg = this lane's image column, W = image width: the side columns are addressed with a per-lane
+// offset clamp(xg +- d, 0, W-1) - xg, which implements replicate padding in x for free (the offset is
+// a register either way), so only rows above / below the image ever need patching in shared memory.
 template <int R, int N>
-__device__ __forceinline__ void compute_pass(const float* (&sp)[CC], uint32_t tbase, float (&acc)[CC][R]) {
+__device__ __forceinline__ void compute_pass(const float* (&sp)[CC], uint32_t tbase, float (&acc)[CC][R], int xg,
+                                             int W) {
     using L = TmemLayout<R>;
 #ifdef PAMR_NO_FFMA2
     constexpr bool kPacked = false;
@@ -303,7 +307,7 @@ __device__ __forceinline__ void compute_pass(const float* (&sp)[CC], uint32_t tb
             if (id < 5) tmem_ld32(tbase + L::SIDE0 + (bi * 6 + id + 1) * 32, ws[(id + 1) & 1]);
             else if (bi == 0) tmem_ld32(tbase + L::SIDE0 + 6 * 32, ws[0]);
             float v[CC][R + 2 * HALO];
-            const int coff = sgn * d;
+            const int coff = min(max(xg + sgn * d, 0), W - 1) - xg;
 #pragma unroll
             for (int r = -d; r < R + d; ++r) {
                 const bool need = (r < R - d) || (r >= 0 && r < R) || (r >= d);
@@ -336,7 +340,8 @@ __device__ __forceinline__ void compute_pass(const float* (&sp)[CC], uint32_t tb
 
 template <int R>
 __device__ __forceinline__ bool needs_patch(int x0, int y0, int H, int W) {
-    return x0 < HALO || y0 < HALO || x0 + TX + HALO > W || y0 + Cfg<R>::TY + HALO > H;
+    (void)x0; (void)W;  // replicate padding in x is handled by the per-lane column offsets
+    return y0 < HALO || y0 + Cfg<R>::TY + HALO > H;
 }
 
 // Border tiles: TMA zero-filled everything outside the image; overwrite it with the clamped
@@ -364,22 +369,6 @@ __device__ __forceinline__ void patch_window(float* slot, int x0, int y0, int H,
                 const float v = slot[(vy1 - 1) * WIN_W + sx];
                 for (int wy = vy1 + wq; wy < WIN_H; wy += NW) slot[wy * WIN_W + wx] = v;
             }
-        }
-    }
-    // in-image rows: columns left / right of the image (one broadcast read per row and side)
-    if (vx0 > 0) {
-#pragma unroll 4
-        for (int wy = vy0 + wq; wy < vy1; wy += NW) {
-            const float v = slot[wy * WIN_W + vx0];
-            if (lane < vx0) slot[wy * WIN_W + lane] = v;
-        }
-    }
-    if (vx1 < WIN_W) {
-#pragma unroll 4
-        for (int wy = vy0 + wq; wy < vy1; wy += NW) {
-            const float v = slot[wy * WIN_W + vx1 - 1];
-            if (vx1 + lane < WIN_W) slot[wy * WIN_W + vx1 + lane] = v;
-            if (vx1 + 32 + lane < WIN_W) slot[wy * WIN_W + vx1 + 32 + lane] = v;
         }
     }
 }
@@ -584,7 +573,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 for (int j = 0; j < CC; ++j)
 #pragma unroll
                     for (int i = 0; i < R; ++i) acc[j][i] = 0.f;
-                compute_pass<R, 1>(sp, tbase, acc);
+                compute_pass<R, 1>(sp, tbase, acc, x, W);
                 PAMR_EV(9);
                 // release the slot as early as possible
                 __syncwarp();

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(416, 1) body_kernel(float* out, int passes, lo
             float acc[CC][R];
             for (int j = 0; j < CC; ++j)
                 for (int i = 0; i < R; ++i) acc[j][i] = 0.f;
-            compute_pass<R, N>(sp, tbase, acc);
+            compute_pass<R, N>(sp, tbase, acc, 64 + lane, 1 << 20);
             for (int j = 0; j < N; ++j)
                 for (int i = 0; i < R; ++i) total += acc[j][i];
         }

@@ -50,6 +50,7 @@ __host__ __device__ constexpr int tap_seq(int p) {
 }
 struct AffTiling {
     int R, tiles_x, tiles_y;  // R rows per thread (tile = 32 x 4R); R == 0: standard [B,48,H,W] layout
+    int Wt, Ht;               // host-side: extent covered by tiles (the rest goes to the strip kernels)
 };
 __host__ __device__ __forceinline__ size_t aff_tiled_floats(int B, const AffTiling& t) {
     return (size_t)B * t.tiles_y * t.tiles_x * 4 * 48 * t.R * 32;
@@ -101,7 +102,7 @@ int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, co
 int launch_aff_relayout(const float* aff_std, float* aff_tiled, int B, int H, int W, const AffTiling& tiling,
                         cudaStream_t s);
 // Tiling of the tuned propagation kernel for this problem; R == 0 when only the generic kernel applies.
-AffTiling tuned_tiling(int H, int W, const Dilations& dil);
+AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil);
 size_t propagate_scratch_bytes(int B, int C, int H, int W, const Dilations& dil, int iters, bool aff_is_tiled);
 int launch_propagate(const float* aff, bool aff_is_tiled, const float* m_in, float* m_out, void* scratch,
                      size_t scratch_bytes, int B, int C, int H, int W, const Dilations& dil, int iters,

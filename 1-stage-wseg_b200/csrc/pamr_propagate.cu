@@ -14,7 +14,6 @@ namespace pamr {
 
 // pamr_propagate_sm100.cu
 int launch_repack(const float* src, float* dst, int planes, int H, int W, int Wp, cudaStream_t s);
-bool tuned_has_strips(int H, int W, const AffTiling& tiling);
 int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, int src_pitch, float* dst,
                            int dst_pitch, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s,
                            cudaStream_t side);
@@ -111,7 +110,7 @@ ScratchPlan plan_scratch(int B, int C, int H, int W, const Dilations& dil, int i
     // strides; W = 321 is not)
     const size_t Wp = align_up((size_t)W, 4);
     p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * H * Wp, 256);
-    const AffTiling t = tuned_tiling(H, W, dil);
+    const AffTiling t = tuned_tiling(B, H, W, dil);
     if (t.R > 0 && !aff_is_tiled) p.aff_tiled = align_up(sizeof(float) * aff_tiled_floats(B, t), 256);
     p.total = 2 * p.pingpong_each + p.aff_tiled;
     return p;
@@ -166,7 +165,7 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
                               const float* m_in, float* m_out, void* scratch, size_t scratch_bytes, int B, int C, int H,
                               int W, const Dilations& dil, int iters, unsigned* cls_max, int dev, cudaStream_t s) {
     const size_t N = (size_t)B * C * H * W;
-    const AffTiling tiling = tuned_tiling(H, W, dil);
+    const AffTiling tiling = tuned_tiling(B, H, W, dil);
     const bool tuned = tiling.R > 0;
     if (cls_max != nullptr) {
         // zeroed by a kernel, not cudaMemsetAsync: a memset node in front of the fork/join events below

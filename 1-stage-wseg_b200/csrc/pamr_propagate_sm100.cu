@@ -405,7 +405,7 @@ __device__ __forceinline__ void strip_item(const Params& prm, int item, int lane
     const int yc = min(y, H - 1), xc = min(x, W - 1);
     const int b = plane / C;
     const float* __restrict__ pl = prm.src + (size_t)plane * H * prm.src_pitch;
-    const AffTiling tl{R, prm.tiles_x_aff, prm.tiles_y_aff};
+    const AffTiling tl{R, prm.tiles_x_aff, prm.tiles_y_aff, 0, 0};
     const float* __restrict__ wp = prm.aff + aff_tiled_index(tl, b, 0, yc, xc);
     float acc = 0.f;
 #pragma unroll
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(SC_CG * 32) strip_cols_kernel(const Params prm
     float* wsm = sc_smem + (size_t)SC_CG * SC_WIN_H * PITCH;
     const int xs0 = W - SC_WIN_W;  // first staged column
     // the weights of the strip pixels: wsm[(xi*48 + s)*32 + row]
-    const AffTiling tl{R, prm.tiles_x_aff, prm.tiles_y_aff};
+    const AffTiling tl{R, prm.tiles_x_aff, prm.tiles_y_aff, 0, 0};
     for (int e = threadIdx.x; e < wc * 48 * SC_ROWS; e += blockDim.x) {
         const int row = e % SC_ROWS, s = (e / SC_ROWS) % 48, xi = e / (SC_ROWS * 48);
         wsm[e] = __ldg(prm.aff + aff_tiled_index(tl, b, s, min(yb + row, H - 1), prm.Wt + xi));
@@ -815,49 +815,52 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
 // subsequent tuned launch fills with {clock64, event code} pairs; nullptr switches it off.
 extern "C" void pamr_debug_set_timeline(long long* dev_buf) { g_timeline.store(dev_buf); }
 
-// Extent handled by the tuned kernel's tiles; a remainder of at most 8 columns / rows goes to the
-// in-kernel strips (producer warp), so that a tile column / row with only a few live pixels is not
-// paid for (W = H = 321 -> 10 x 8 tiles of 32 x 40 plus one column and one row).
-static int strip_max() {  // largest remainder (pixels) handled as a strip; PAMR_B200_STRIP_MAX overrides
-    static const int v = getenv("PAMR_B200_STRIP_MAX") ? atoi(getenv("PAMR_B200_STRIP_MAX")) : 8;
-    return v;
-}
-int tuned_width(int W) {
-    const int rem = W % TX;
-    return (rem != 0 && rem <= strip_max() && W > TX) ? W - rem : W;
-}
-int tuned_height(int H, int R) {
-    const int ty = NW * R, rem = H % ty;
-    return (rem != 0 && rem <= strip_max() && H > ty) ? H - rem : H;
-}
-
-// Tiling of the tuned kernel (R rows per thread, tile = 32 x 4R) or R == 0 when it does not apply.
-AffTiling tuned_tiling(int H, int W, const Dilations& dil) {
+// Tiling of the tuned kernel (R rows per thread, tile = 32 x 4R, extent [0,Wt) x [0,Ht) covered by
+// tiles, remainders of at most 8 columns / rows by the strip kernels) or R == 0 when the tuned kernel
+// does not apply.  All combinations (R in {8,9,10}) x (row remainder: strip | padded tile row) x
+// (column remainder: strip | partial tile column) are priced with a small time model fitted to
+// measurements on B200 -- waves of tiles over the SMs, ~2.8 us per tile row-of-pixels-per-thread,
+// ~15 us per row-strip launch, ~32 us per column-strip launch -- and the cheapest wins.  E.g. 321 x 321,
+// B=16: R=10, 10 x 8 tiles + one strip column + one strip row; 256 x 256, B=1: R=8, no strips.
+// Experiment overrides: PAMR_B200_ROWS=8|9|10, PAMR_B200_STRIP_MAX=<pixels> (0 disables strips).
+AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
     static const int want[6] = {1, 2, 4, 8, 12, 24};
     // debugging / A-B aid: PAMR_B200_FORCE_GENERIC=1 routes everything to the generic CUDA kernel
     static const bool force_generic = []() {
         const char* e = getenv("PAMR_B200_FORCE_GENERIC");
         return e != nullptr && e[0] == '1';
     }();
-    AffTiling t{0, 0, 0};
+    static const int force_rows = getenv("PAMR_B200_ROWS") ? atoi(getenv("PAMR_B200_ROWS")) : 0;
+    static const int strip_max = getenv("PAMR_B200_STRIP_MAX") ? atoi(getenv("PAMR_B200_STRIP_MAX")) : 8;
+    AffTiling t{0, 0, 0, 0, 0};
     if (force_generic || dil.nd != 6 || W < TX || H < 8) return t;
     for (int i = 0; i < 6; ++i)
         if (dil.d[i] != want[i]) return t;
-    // Rows per thread: the packed-FFMA2 body needs an even R (measured cycles per pixel-class:
-    // R=10 1.11, R=8 1.19; the scalar R=9 body is ~2x slower), so pick the even R with the
-    // least (padded rows x cost per row).  PAMR_B200_ROWS=8|9|10 overrides (experiments).
-    static const int force_rows = getenv("PAMR_B200_ROWS") ? atoi(getenv("PAMR_B200_ROWS")) : 0;
-    int best = 10;
+    const int sms = 148;
     double best_cost = 1e30;
     for (int r = 8; r <= 10; ++r) {
-        const int ty = NW * r, ht = tuned_height(H, r);
-        const double cost = (double)((ht + ty - 1) / ty * ty) * (r == 10 ? 1.11 : r == 9 ? 1.13 : 1.19);
-        if (cost < best_cost) { best = r; best_cost = cost; }
+        if (force_rows >= 8 && force_rows <= 10 && r != force_rows) continue;
+        const int ty = NW * r;
+        const double tile_us = 2.8 * r * (r == 10 ? 1.00 : r == 9 ? 1.02 : 1.07);
+        for (int rs = 0; rs < 2; ++rs) {      // rs: row remainder as a strip
+            const int hrem = H % ty;
+            if (rs && !(hrem != 0 && hrem <= strip_max && H > ty)) continue;
+            const int ht = rs ? H - hrem : H;
+            for (int cs = 0; cs < 2; ++cs) {  // cs: column remainder as a strip
+                const int wrem = W % TX;
+                if (cs && !(wrem != 0 && wrem <= strip_max && W > TX)) continue;
+                const int wt = cs ? W - wrem : W;
+                const long long ntiles = (long long)B * ((wt + TX - 1) / TX) * ((ht + ty - 1) / ty);
+                const double cost = (double)((ntiles + sms - 1) / sms) * tile_us + (rs ? 15.0 : 0.0) + (cs ? 32.0 : 0.0);
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    t.R = r; t.Wt = wt; t.Ht = ht;
+                }
+            }
+        }
     }
-    if (force_rows >= 8 && force_rows <= 10) best = force_rows;
-    t.R = best;
     t.tiles_x = (W + TX - 1) / TX;
-    t.tiles_y = (H + NW * best - 1) / (NW * best);
+    t.tiles_y = (H + NW * t.R - 1) / (NW * t.R);
     return t;
 }
 
@@ -870,14 +873,8 @@ int launch_repack(const float* src, float* dst, int planes, int H, int W, int Wp
     return PAMR_OK;
 }
 
-// One propagation step src -> dst with the tuned kernel over x in [0, tuned_width(W)).
-// src must have a pitch that is a multiple of 4 floats and a 16-byte aligned base.
-bool tuned_has_strips(int H, int W, const AffTiling& tiling) {
-    return tuned_width(W) < W || tuned_height(H, tiling.R) < H;
-}
-
-// `side`: stream (already ordered after the producer of `src`) for the remainder-strip launch, or
-// nullptr to let the persistent kernel's producer warp compute the strips itself.
+// One propagation step src -> dst: the strip kernels (if the tiling has remainders) followed by the
+// persistent tile kernel.  src must have a pitch that is a multiple of 4 floats and a 16-byte aligned base.
 int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, int src_pitch, float* dst,
                            int dst_pitch, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s,
                            cudaStream_t side) {
@@ -889,7 +886,7 @@ int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, cons
     }
     if ((src_pitch & 3) != 0 || ((uintptr_t)src & 15) != 0)
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: source pitch/base not 16-byte aligned");
-    const int Wt = tuned_width(W), Ht = tuned_height(H, tiling.R);
+    const int Wt = tiling.Wt, Ht = tiling.Ht;
     if (tiling.R == 8) return launch_one<8>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, side);
     if (tiling.R == 9) return launch_one<9>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, side);
     return launch_one<10>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, side);

@@ -841,7 +841,9 @@ AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
     for (int r = 8; r <= 10; ++r) {
         if (force_rows >= 8 && force_rows <= 10 && r != force_rows) continue;
         const int ty = NW * r;
-        const double tile_us = 2.8 * r * (r == 10 ? 1.00 : r == 9 ? 1.02 : 1.07);
+        // R = 9 (odd: scalar tail row, spills at 128 registers) measured ~2x slower per tile: kept for
+        // experiments, effectively never chosen
+        const double tile_us = 2.8 * r * (r == 10 ? 1.00 : r == 9 ? 2.2 : 1.07);
         for (int rs = 0; rs < 2; ++rs) {      // rs: row remainder as a strip
             const int hrem = H % ty;
             if (rs && !(hrem != 0 && hrem <= strip_max && H > ty)) continue;

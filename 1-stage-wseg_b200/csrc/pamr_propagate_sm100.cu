@@ -25,6 +25,7 @@
 #include <cuda.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 
@@ -40,7 +41,7 @@ constexpr int WIN_W = TX + 2 * HALO;  // 80 floats = 320 B rows in shared memory
 constexpr int NW = 4;                 // warps per compute group (= TMEM lane quarters)
 constexpr int NG = 3;                 // compute groups that share the tile's weights in TMEM (class c -> group c % NG)
 constexpr int NWC = NG * NW;          // compute warps
-constexpr int NSLOT = 8;              // class-plane slots in the shared-memory ring
+constexpr int NSLOT = 4;              // class-plane slots in the shared-memory ring
 #ifndef PAMR_CC
 #define PAMR_CC 1
 #endif
@@ -151,6 +152,8 @@ struct Params {
     int src_pitch;
     int Wt, Ht;                    // the tiles cover [0,Wt) x [0,Ht); the producer warp computes the remainder strips
     int strip_items;               // number of 32-pixel strip work items (all CTAs together)
+    int tail_cta0;                 // row strip inside the tile kernel: CTAs >= tail_cta0 (one tile fewer than the
+                                   // others) work through the strip_items row items after their last tile; -1: off
 };
 
 // ---------------------------------------------------------------- TMEM weight layout
@@ -385,21 +388,21 @@ __device__ __forceinline__ void compute_bar_sync() {  // the NWC compute warps o
 // otherwise 32 columns of one strip row -- which the compute warps pick up at tile boundaries
 // (one pixel per lane, neighbours and weights straight from global memory / L2, clamped coordinates).
 template <int R>
-__device__ __forceinline__ void strip_item(const Params& prm, int item, int lane) {
+__device__ __forceinline__ void strip_item(const Params& prm, const int Wt, int item, int lane) {
     const int C = prm.C, H = prm.H, W = prm.W;
-    const int wcols = W - prm.Wt, hrows = H - prm.Ht;
-    const int yblocks = (H + 31) / 32, xblocks = (prm.Wt + 31) / 32;
+    const int wcols = W - Wt, hrows = H - prm.Ht;
+    const int yblocks = (H + 31) / 32, xblocks = (Wt + 31) / 32;
     const int per_plane = wcols * yblocks + hrows * xblocks;
     const int plane = item / per_plane, r = item % per_plane;  // plane = b*C + c
     int x, y;
     if (r < wcols * yblocks) {
-        x = prm.Wt + r / yblocks;
+        x = Wt + r / yblocks;
         y = (r % yblocks) * 32 + lane;
     } else {
         const int q = r - wcols * yblocks;
         y = prm.Ht + q / xblocks;
         x = (q % xblocks) * 32 + lane;
-        if (x >= prm.Wt) x = W;  // beyond the row strip (those columns belong to the column strip)
+        if (x >= Wt) x = W;  // beyond the row strip (those columns belong to the column strip)
     }
     const bool valid = (y < H) && (x < W);
     const int yc = min(y, H - 1), xc = min(x, W - 1);
@@ -407,16 +410,13 @@ __device__ __forceinline__ void strip_item(const Params& prm, int item, int lane
     const float* __restrict__ pl = prm.src + (size_t)plane * H * prm.src_pitch;
     const AffTiling tl{R, prm.tiles_x_aff, prm.tiles_y_aff, 0, 0};
     const float* __restrict__ wp = prm.aff + aff_tiled_index(tl, b, 0, yc, xc);
-    float acc = 0.f;
+    float acc = 0.f;  // one FMA chain in tap-sequence order: bit-identical to the tile kernel's result
 #pragma unroll
-    for (int id = 0; id < 6; ++id) {
-        const int d = dil_of(id);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int yy = clampi(yc + tap_dy(j) * d, 0, H - 1);
-            const int xx = clampi(xc + tap_dx(j) * d, 0, W - 1);
-            acc = fmaf(__ldg(wp + tap_seq(8 * id + j) * (R * 32)), __ldg(pl + (size_t)yy * prm.src_pitch + xx), acc);
-        }
+    for (int s = 0; s < 48; ++s) {
+        const int p = seq_tap(s), d = dil_of(p >> 3), j = p & 7;
+        const int yy = clampi(yc + tap_dy(j) * d, 0, H - 1);
+        const int xx = clampi(xc + tap_dx(j) * d, 0, W - 1);
+        acc = fmaf(__ldg(wp + s * (R * 32)), __ldg(pl + (size_t)yy * prm.src_pitch + xx), acc);
     }
     if (valid) prm.dst[((size_t)plane * H + y) * prm.dst_pitch + x] = acc;
     if (prm.cls_max != nullptr) {
@@ -612,6 +612,13 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             }
         }
 #undef PAMR_EV
+        // ---- row strip in the tail: the CTAs that own one tile fewer than the rest would idle during
+        //      the last wave; they compute the row strip y in [Ht,H) instead (no separate launch)
+        if (prm.tail_cta0 >= 0 && (int)blockIdx.x >= prm.tail_cta0) {
+            const int nw = ((int)gridDim.x - prm.tail_cta0) * NWC;
+            for (int item = ((int)blockIdx.x - prm.tail_cta0) * NWC + warp; item < prm.strip_items; item += nw)
+                strip_item<R>(prm, W, item, lane);
+        }
     }
 
     __syncthreads();
@@ -630,7 +637,7 @@ template <int R>
 __global__ void __launch_bounds__(128) strip_rows_kernel(const Params prm) {
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < prm.strip_items; item += gridDim.x * wpb)
-        strip_item<R>(prm, item, lane);
+        strip_item<R>(prm, prm.Wt, item, lane);
 }
 
 // Column strip: x in [Wt,W), all y.  Neighbours of a column of pixels lie in different rows, i.e.
@@ -640,7 +647,7 @@ __global__ void __launch_bounds__(128) strip_rows_kernel(const Params prm) {
 constexpr int SC_ROWS = 32;                      // pixel rows per CTA
 constexpr int SC_WIN_H = SC_ROWS + 2 * HALO;     // 80
 constexpr int SC_WIN_W = 32;                     // staged columns [W-32, W)  (needs W >= 32)
-constexpr int SC_CG = 16;                        // class planes staged at a time (one warp each)
+constexpr int SC_CG = 8;                         // class planes staged at a time (one warp each)
 template <int R>
 __global__ void __launch_bounds__(SC_CG * 32) strip_cols_kernel(const Params prm) {
     extern __shared__ float sc_smem[];  // [SC_CG][SC_WIN_H][SC_WIN_W + 1] then weights [wc][48][32]
@@ -675,15 +682,12 @@ __global__ void __launch_bounds__(SC_CG * 32) strip_cols_kernel(const Params prm
             const float* win = mywin + (lane + HALO) * PITCH;
             for (int xi = 0; xi < wc; ++xi) {
                 const int xl = prm.Wt + xi - xs0;  // column inside the staged window
-                float acc = 0.f;
+                float acc = 0.f;  // tap-sequence order, like the tile kernel (bit-identical results)
 #pragma unroll
-                for (int id = 0; id < 6; ++id) {
-                    const int d = dil_of(id);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int xx = min(xl + tap_dx(j) * d, SC_WIN_W - 1);  // clamp at the right image border
-                        acc = fmaf(wsm[(xi * 48 + tap_seq(8 * id + j)) * SC_ROWS + lane], win[tap_dy(j) * d * PITCH + xx], acc);
-                    }
+                for (int sq = 0; sq < 48; ++sq) {
+                    const int p = seq_tap(sq), d = dil_of(p >> 3), j = p & 7;
+                    const int xx = min(xl + tap_dx(j) * d, SC_WIN_W - 1);  // clamp at the right image border
+                    acc = fmaf(wsm[(xi * 48 + sq) * SC_ROWS + lane], win[tap_dy(j) * d * PITCH + xx], acc);
                 }
                 const bool valid = y < H;
                 if (valid) prm.dst[(((size_t)b * C + c) * H + y) * prm.dst_pitch + prm.Wt + xi] = acc;
@@ -740,6 +744,17 @@ int make_tmap(CUtensorMap* map, const float* base, int planes, int H, int W, int
     return PAMR_OK;
 }
 
+// Row strip placement: when the tile count leaves the last wave partly empty, the CTAs without a
+// tile in that wave take the row-strip items (one warp per item, ~2.5 us each, TAIL_ITEMS_MAX in a
+// row still fit inside one tile time); otherwise the strip is a launch of its own.
+constexpr int TAIL_ITEMS_MAX = 8;
+inline bool row_strip_in_tail(long long items, int ntiles, int grid) {
+    static const bool off = getenv("PAMR_B200_NO_TAIL") != nullptr;
+    if (off || grid <= 0 || ntiles <= grid || ntiles % grid == 0) return false;
+    const long long warps = (long long)(grid - ntiles % grid) * NWC;
+    return (items + warps - 1) / warps <= TAIL_ITEMS_MAX;
+}
+
 template <int R>
 int launch_one(const float* aff, const AffTiling& tiling, const float* src, int src_pitch, float* dst, int dst_pitch,
                int B, int C, int H, int W, int Wt, int Ht, unsigned* cls_max, int sm_count, cudaStream_t s,
@@ -775,13 +790,20 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
     p.tiles_y_aff = tiling.tiles_y;
     p.src = src; p.src_pitch = src_pitch; p.Wt = Wt; p.Ht = Ht;
     p.strip_items = 0;
+    p.tail_cta0 = -1;
+    p.ntiles = p.tiles_x * p.tiles_y * B;
+    const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
     const bool skip_strips = getenv("PAMR_B200_EXPERIMENT") && (atoi(getenv("PAMR_B200_EXPERIMENT")) & 16);
-    if (Ht < H && !skip_strips) {  // row strip y in [Ht,H), all columns
+    const long long row_items = (long long)B * C * (H - Ht) * ((W + 31) / 32);
+    if (row_items > 0x7fffffffLL) return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: row strip too large");
+    if (Ht < H && !skip_strips && row_strip_in_tail(row_items, p.ntiles, grid)) {
+        p.strip_items = (int)row_items;  // the tile kernel's short CTAs do the row strip
+        p.tail_cta0 = p.ntiles % grid;
+    } else if (Ht < H && !skip_strips) {  // row strip y in [Ht,H), all columns, as a launch of its own
         Params pr = p;
         pr.Wt = W;  // strip_item: no column part, the row part spans [0,W)
-        const long long items = (long long)B * C * (H - Ht) * ((W + 31) / 32);
-        if (items > 0x7fffffffLL) return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: row strip too large");
-        pr.strip_items = (int)items;
+        pr.strip_items = (int)row_items;
+        const long long items = row_items;
         const int blocks = (int)((items + 3) / 4);
         strip_rows_kernel<R><<<blocks < 8 * sm_count ? blocks : 8 * sm_count, 128, 0, s>>>(pr);
         count_launch();
@@ -799,8 +821,6 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
         count_launch();
         PAMR_CUDA_TRY(cudaGetLastError());
     }
-    p.ntiles = p.tiles_x * p.tiles_y * B;
-    const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
     Params pm = p;
     (void)side;
     propagate_sm100_kernel<R><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, pm);
@@ -816,13 +836,20 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
 extern "C" void pamr_debug_set_timeline(long long* dev_buf) { g_timeline.store(dev_buf); }
 
 // Tiling of the tuned kernel (R rows per thread, tile = 32 x 4R, extent [0,Wt) x [0,Ht) covered by
-// tiles, remainders of at most 8 columns / rows by the strip kernels) or R == 0 when the tuned kernel
-// does not apply.  All combinations (R in {8,9,10}) x (row remainder: strip | padded tile row) x
-// (column remainder: strip | partial tile column) are priced with a small time model fitted to
-// measurements on B200 -- waves of tiles over the SMs, ~2.8 us per tile row-of-pixels-per-thread,
-// ~15 us per row-strip launch, ~32 us per column-strip launch -- and the cheapest wins.  E.g. 321 x 321,
-// B=16: R=10, 10 x 8 tiles + one strip column + one strip row; 256 x 256, B=1: R=8, no strips.
-// Experiment overrides: PAMR_B200_ROWS=8|9|10, PAMR_B200_STRIP_MAX=<pixels> (0 disables strips).
+// tiles) or R == 0 when the tuned kernel does not apply.  Remainders of at most 8 rows / columns have
+// an alternative to a padded tile row / partial tile column:
+//   rows:    the row strip -- inside the tile kernel's last wave when that wave has idle CTAs
+//            (row_strip_in_tail), else a launch of its own;
+//   columns: the column-strip launch.
+// All combinations with R in {8,9,10} are priced with a time model fitted to measurements on B200
+// (profiles/r01_strip_times.txt): waves of tiles over the SMs at ~2.8 us per row-per-thread, row-strip
+// launch ~ 8 + 1.3 us per 1000 items, column-strip launch ~ (10 + 2.1 wc) * max(1, CTAs/90)^0.8 us -- and
+// the cheapest wins.  E.g. 321 x 321, B=16: R=10, 11 x 8 tiles (the last column partial), row 320 in the
+// tail of the same launch.  All paths add the 48 products of a pixel in the same order, so the result
+// does not depend on the tiling (nor, therefore, on how a batch is sharded).
+// Experiment overrides: PAMR_B200_ROWS=8|9|10, PAMR_B200_STRIP_MAX=<pixels> (0 disables strips),
+// PAMR_B200_FORCE_STRIPS (bit 0 rows, bit 1 columns: take the strip whenever it qualifies),
+// PAMR_B200_NO_TAIL=1.
 AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
     static const int want[6] = {1, 2, 4, 8, 12, 24};
     // debugging / A-B aid: PAMR_B200_FORCE_GENERIC=1 routes everything to the generic CUDA kernel
@@ -832,11 +859,12 @@ AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
     }();
     static const int force_rows = getenv("PAMR_B200_ROWS") ? atoi(getenv("PAMR_B200_ROWS")) : 0;
     static const int strip_max = getenv("PAMR_B200_STRIP_MAX") ? atoi(getenv("PAMR_B200_STRIP_MAX")) : 8;
+    static const int force_strips = getenv("PAMR_B200_FORCE_STRIPS") ? atoi(getenv("PAMR_B200_FORCE_STRIPS")) : 0;
     AffTiling t{0, 0, 0, 0, 0};
     if (force_generic || dil.nd != 6 || W < TX || H < 8) return t;
     for (int i = 0; i < 6; ++i)
         if (dil.d[i] != want[i]) return t;
-    const int sms = 148;
+    const int sms = 148, C = 21;  // the model prices the reference's 21 classes
     double best_cost = 1e30;
     for (int r = 8; r <= 10; ++r) {
         if (force_rows >= 8 && force_rows <= 10 && r != force_rows) continue;
@@ -844,16 +872,27 @@ AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
         // R = 9 (odd: scalar tail row, spills at 128 registers) measured ~2x slower per tile: kept for
         // experiments, effectively never chosen
         const double tile_us = 2.8 * r * (r == 10 ? 1.00 : r == 9 ? 2.2 : 1.07);
+        const int hrem = H % ty, wrem = W % TX;
+        const bool rs_ok = hrem != 0 && hrem <= strip_max && H > ty;
+        const bool cs_ok = wrem != 0 && wrem <= strip_max && W > TX;
         for (int rs = 0; rs < 2; ++rs) {      // rs: row remainder as a strip
-            const int hrem = H % ty;
-            if (rs && !(hrem != 0 && hrem <= strip_max && H > ty)) continue;
+            if (rs ? !rs_ok : (rs_ok && (force_strips & 1))) continue;
             const int ht = rs ? H - hrem : H;
-            for (int cs = 0; cs < 2; ++cs) {  // cs: column remainder as a strip
-                const int wrem = W % TX;
-                if (cs && !(wrem != 0 && wrem <= strip_max && W > TX)) continue;
+            for (int cs = 0; cs < 2; ++cs) {  // cs: column remainder as a strip launch
+                if (cs ? !cs_ok : (cs_ok && (force_strips & 2))) continue;
                 const int wt = cs ? W - wrem : W;
                 const long long ntiles = (long long)B * ((wt + TX - 1) / TX) * ((ht + ty - 1) / ty);
-                const double cost = (double)((ntiles + sms - 1) / sms) * tile_us + (rs ? 15.0 : 0.0) + (cs ? 32.0 : 0.0);
+                if (ntiles > 0x7fffffffLL) continue;
+                double cost = (double)((ntiles + sms - 1) / sms) * tile_us;
+                if (rs) {
+                    const long long items = (long long)B * C * hrem * ((W + 31) / 32);
+                    const int grid = ntiles < sms ? (int)ntiles : sms;
+                    if (!row_strip_in_tail(items, (int)ntiles, grid)) cost += 8.0 + 1.3e-3 * (double)items;
+                }
+                if (cs) {
+                    const double ctas = (double)B * ((H + SC_ROWS - 1) / SC_ROWS);
+                    cost += (10.0 + 2.1 * wrem) * pow(ctas > 90.0 ? ctas / 90.0 : 1.0, 0.8);
+                }
                 if (cost < best_cost) {
                     best_cost = cost;
                     t.R = r; t.Wt = wt; t.Ht = ht;

@@ -101,6 +101,14 @@ int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, co
                     const AffTiling& tiling, cudaStream_t s);
 int launch_aff_relayout(const float* aff_std, float* aff_tiled, int B, int H, int W, const AffTiling& tiling,
                         cudaStream_t s);
+// Second stream on which the column-strip kernel of iteration t runs concurrently with the tile kernel
+// of iteration t (both only depend on iteration t-1); two reusable events order the iterations.
+struct SideLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t tiles_done = nullptr;  // recorded on the main stream after each tile launch (and once before the first)
+    cudaEvent_t strip_done = nullptr;  // recorded on `stream` after each column-strip launch
+    bool strip_pending = false;        // strip_done holds a launch the main stream has not waited for yet
+};
 // Tiling of the tuned propagation kernel for this problem; R == 0 when only the generic kernel applies.
 AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil);
 size_t propagate_scratch_bytes(int B, int C, int H, int W, const Dilations& dil, int iters, bool aff_is_tiled);

@@ -16,7 +16,7 @@ namespace pamr {
 int launch_repack(const float* src, float* dst, int planes, int H, int W, int Wp, cudaStream_t s);
 int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, int src_pitch, float* dst,
                            int dst_pitch, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s,
-                           cudaStream_t side);
+                           SideLane* lane);
 
 namespace {
 
@@ -124,7 +124,7 @@ ScratchPlan plan_scratch(int B, int C, int H, int W, const Dilations& dil, int i
 // registers for these, so their time disappears from the critical path.
 struct ForkJoin {
     cudaStream_t main_s = nullptr, side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_tiles = nullptr, ev_strip = nullptr;
     int init(int dev, cudaStream_t m) {
         static thread_local cudaStream_t cache[64] = {nullptr};
         main_s = m;
@@ -136,6 +136,8 @@ struct ForkJoin {
         }
         PAMR_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         PAMR_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&ev_tiles, cudaEventDisableTiming));
+        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&ev_strip, cudaEventDisableTiming));
         return PAMR_OK;
     }
     int fork() {  // work enqueued on `side` after this sees everything enqueued on main so far
@@ -151,6 +153,8 @@ struct ForkJoin {
     ~ForkJoin() {
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_tiles) cudaEventDestroy(ev_tiles);
+        if (ev_strip) cudaEventDestroy(ev_strip);
     }
 };
 
@@ -201,8 +205,9 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: tiled affinity without the tuned kernel");
     const bool need_repack = tuned && ((W & 3) != 0 || ((uintptr_t)m_in & 15) != 0);
 
+    const bool col_strip = tuned && tiling.Wt < W;  // runs on the side stream, concurrently with the tiles
     ForkJoin fj;
-    if (need_repack) {
+    if (need_repack || col_strip) {
         int rc = fj.init(dev, s);
         if (rc != PAMR_OK) return rc;
     }
@@ -228,6 +233,13 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
     }
     if (need_repack && (rc = fj.join()) != PAMR_OK) return rc;
 
+    SideLane lane;
+    if (col_strip) {
+        lane.stream = fj.side;
+        lane.tiles_done = fj.ev_tiles;
+        lane.strip_done = fj.ev_strip;
+        PAMR_CUDA_TRY(cudaEventRecord(lane.tiles_done, s));  // the first strip waits for affinity / repack
+    }
     for (int it = 0; it < iters; ++it) {
         const bool last = (it == iters - 1);
         float* dst = last ? m_out : P[next];
@@ -235,7 +247,8 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
         unsigned* mx = last ? cls_max : nullptr;
         if (tuned) {
             // (remainder columns / rows are computed inside the same launch, at tile boundaries)
-            rc = launch_propagate_tuned(aff, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, mx, dev, s, nullptr);
+            rc = launch_propagate_tuned(aff, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, mx, dev, s,
+                                        col_strip ? &lane : nullptr);
         } else {
             rc = launch_generic(aff, src, src_pitch, dst, dst_pitch, B, C, H, W, dil, mx, s);
         }
@@ -244,6 +257,7 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
         src_pitch = dst_pitch;
         next ^= 1;
     }
+    if (lane.strip_pending) PAMR_CUDA_TRY(cudaStreamWaitEvent(s, lane.strip_done, 0));  // join the last strip
     return PAMR_OK;
 }
 

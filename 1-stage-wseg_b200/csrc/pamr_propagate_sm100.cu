@@ -561,7 +561,11 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 if (!probe && !(prm.exp_flags & 8)) mbar_wait(smem_u32(&ctrl->tma_bar[s]), par);  // bytes landed
                 if (border && !(prm.exp_flags & 4)) {  // replicate padding: the group patches the halo of its own slot
                     patch_window<R>(slots + (size_t)s * C_::SLOT_FLOATS, x0, y0, H, W, wq, lane);
-                    asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(NW * 32) : "memory");
+                    // immediate barrier ids: with a register id ptxas reserves all 16 named barriers and no
+                    // other CTA (the concurrent column strip) could share the SM
+                    if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(NW * 32) : "memory");
+                    else if (grp == 1) asm volatile("bar.sync 3, %0;" ::"n"(NW * 32) : "memory");
+                    else asm volatile("bar.sync 4, %0;" ::"n"(NW * 32) : "memory");
                 }
                 const float* sp[CC];
 #pragma unroll
@@ -649,7 +653,7 @@ constexpr int SC_WIN_H = SC_ROWS + 2 * HALO;     // 80
 constexpr int SC_WIN_W = 32;                     // staged columns [W-32, W)  (needs W >= 32)
 constexpr int SC_CG = 8;                         // class planes staged at a time (one warp each)
 template <int R>
-__global__ void __launch_bounds__(SC_CG * 32) strip_cols_kernel(const Params prm) {
+__global__ void __launch_bounds__(SC_CG * 32, 6) strip_cols_kernel(const Params prm) {  // (.,6): <= 40 registers
     extern __shared__ float sc_smem[];  // [SC_CG][SC_WIN_H][SC_WIN_W + 1] then weights [wc][48][32]
     const int C = prm.C, H = prm.H, W = prm.W, wc = W - prm.Wt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -669,13 +673,17 @@ __global__ void __launch_bounds__(SC_CG * 32) strip_cols_kernel(const Params prm
         const int c = c0 + warp;
         if (c < C) {  // stage this warp's class plane window (rows clamped: replicate padding)
             const float* __restrict__ pl = prm.src + ((size_t)b * C + c) * H * prm.src_pitch;
-            // all 80 row loads in flight at once (latency-, not bandwidth-bound)
-            float v[SC_WIN_H];
+            // 8 row loads in flight at a time: the kernel overlaps the tile kernel on a second stream and is
+            // kept small in registers so that its CTAs can be placed as soon as an SM has room
+#pragma unroll 1
+            for (int r0 = 0; r0 < SC_WIN_H; r0 += 8) {
+                float v[8];
 #pragma unroll
-            for (int r = 0; r < SC_WIN_H; ++r)
-                v[r] = __ldg(pl + (size_t)clampi(yb - HALO + r, 0, H - 1) * prm.src_pitch + xs0 + lane);
+                for (int q = 0; q < 8; ++q)
+                    v[q] = __ldg(pl + (size_t)clampi(yb - HALO + r0 + q, 0, H - 1) * prm.src_pitch + xs0 + lane);
 #pragma unroll
-            for (int r = 0; r < SC_WIN_H; ++r) mywin[r * PITCH + lane] = v[r];
+                for (int q = 0; q < 8; ++q) mywin[(r0 + q) * PITCH + lane] = v[q];
+            }
         }
         __syncthreads();  // also covers the weights on the first round
         if (c < C) {
@@ -758,7 +766,7 @@ inline bool row_strip_in_tail(long long items, int ntiles, int grid) {
 template <int R>
 int launch_one(const float* aff, const AffTiling& tiling, const float* src, int src_pitch, float* dst, int dst_pitch,
                int B, int C, int H, int W, int Wt, int Ht, unsigned* cls_max, int sm_count, cudaStream_t s,
-               cudaStream_t side) {
+               SideLane* lane) {
     using C_ = Cfg<R>;
     // function attributes are per device: set once per (kernel, device)
     static std::atomic<int> attr_set[64];
@@ -794,6 +802,11 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
     p.ntiles = p.tiles_x * p.tiles_y * B;
     const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
     const bool skip_strips = getenv("PAMR_B200_EXPERIMENT") && (atoi(getenv("PAMR_B200_EXPERIMENT")) & 16);
+    const bool col_strip = Wt < W && !skip_strips;
+    if (col_strip && lane != nullptr && lane->strip_pending) {  // this iteration reads what strip(t-1) wrote
+        PAMR_CUDA_TRY(cudaStreamWaitEvent(s, lane->strip_done, 0));
+        lane->strip_pending = false;
+    }
     const long long row_items = (long long)B * C * (H - Ht) * ((W + 31) / 32);
     if (row_items > 0x7fffffffLL) return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: row strip too large");
     if (Ht < H && !skip_strips && row_strip_in_tail(row_items, p.ntiles, grid)) {
@@ -809,23 +822,38 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
         count_launch();
         PAMR_CUDA_TRY(cudaGetLastError());
     }
-    if (Wt < W && !skip_strips) {  // column strip x in [Wt,W), all rows
+    // The column strip (x in [Wt,W), all rows) runs on the side lane concurrently with the tile kernel:
+    // both only read iteration t-1.  Measured on B200 its CTAs mostly get placed as tile CTAs retire in
+    // the last wave (side-stream CTAs are scheduled only sluggishly next to resident persistent CTAs,
+    // tools/coresidency.py), which still hides about half of it: 321x321 B=16 forward 3.085 ms vs
+    // 3.204 ms with the strip serialised.  Ordering: the main stream waited for strip(t-1) above
+    // (iteration t reads and overwrites what that strip wrote / read); strip(t) waits for tiles(t-1).
+    Params pm = p;
+    propagate_sm100_kernel<R><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, pm);
+    count_launch();
+    PAMR_CUDA_TRY(cudaGetLastError());
+    if (col_strip) {
         const size_t smem = sizeof(float) * ((size_t)SC_CG * SC_WIN_H * (SC_WIN_W + 1) + (size_t)(W - Wt) * 48 * SC_ROWS);
         static std::atomic<int> sc_attr[64];
         if (dev >= 64 || sc_attr[dev].load(std::memory_order_acquire) == 0) {
             PAMR_CUDA_TRY(cudaFuncSetAttribute(strip_cols_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             if (dev < 64) sc_attr[dev].store(1, std::memory_order_release);
         }
-        dim3 grid((H + SC_ROWS - 1) / SC_ROWS, B);
-        strip_cols_kernel<R><<<grid, SC_CG * 32, smem, s>>>(p);
+        dim3 sgrid((H + SC_ROWS - 1) / SC_ROWS, B);
+        cudaStream_t ss = s;
+        if (lane != nullptr) {
+            ss = lane->stream;
+            PAMR_CUDA_TRY(cudaStreamWaitEvent(ss, lane->tiles_done, 0));  // tiles(t-1) (or the prologue) finished
+        }
+        strip_cols_kernel<R><<<sgrid, SC_CG * 32, smem, ss>>>(p);
         count_launch();
         PAMR_CUDA_TRY(cudaGetLastError());
+        if (lane != nullptr) {
+            PAMR_CUDA_TRY(cudaEventRecord(lane->strip_done, ss));
+            lane->strip_pending = true;
+            PAMR_CUDA_TRY(cudaEventRecord(lane->tiles_done, s));  // tiles(t), for strip(t+1)
+        }
     }
-    Params pm = p;
-    (void)side;
-    propagate_sm100_kernel<R><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, pm);
-    count_launch();
-    PAMR_CUDA_TRY(cudaGetLastError());
     return PAMR_OK;
 }
 
@@ -843,9 +871,9 @@ extern "C" void pamr_debug_set_timeline(long long* dev_buf) { g_timeline.store(d
 //   columns: the column-strip launch.
 // All combinations with R in {8,9,10} are priced with a time model fitted to measurements on B200
 // (profiles/r01_strip_times.txt): waves of tiles over the SMs at ~2.8 us per row-per-thread, row-strip
-// launch ~ 8 + 1.3 us per 1000 items, column-strip launch ~ (10 + 2.1 wc) * max(1, CTAs/90)^0.8 us -- and
-// the cheapest wins.  E.g. 321 x 321, B=16: R=10, 11 x 8 tiles (the last column partial), row 320 in the
-// tail of the same launch.  All paths add the 48 products of a pixel in the same order, so the result
+// launch ~ 8 + 1.3 us per 1000 items, column-strip launch ~ (12 + 2.6 wc) * max(1, CTAs/90)^0.8 us minus what
+// hides in the last wave -- and the cheapest wins.  E.g. 321 x 321, B=16: R=10, 10 x 8 tiles, row 320 in the
+// tail of the same launch, column 320 as a strip launch on the side lane.  All paths add the 48 products of a pixel in the same order, so the result
 // does not depend on the tiling (nor, therefore, on how a batch is sharded).
 // Experiment overrides: PAMR_B200_ROWS=8|9|10, PAMR_B200_STRIP_MAX=<pixels> (0 disables strips),
 // PAMR_B200_FORCE_STRIPS (bit 0 rows, bit 1 columns: take the strip whenever it qualifies),
@@ -891,7 +919,12 @@ AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
                 }
                 if (cs) {
                     const double ctas = (double)B * ((H + SC_ROWS - 1) / SC_ROWS);
-                    cost += (10.0 + 2.1 * wrem) * pow(ctas > 90.0 ? ctas / 90.0 : 1.0, 0.8);
+                    // stand-alone duration, less what hides in the idle part of the tile kernel's last wave
+                    // (the strip runs on the side lane and its CTAs land on SMs whose tile CTA has retired)
+                    const double alone = (12.0 + 2.6 * wrem) * pow(ctas > 90.0 ? ctas / 90.0 : 1.0, 0.8);
+                    const double waves = (double)((ntiles + sms - 1) / sms);
+                    const double idle_us = (waves * sms - (double)ntiles) / sms * tile_us;
+                    cost += fmax(0.25 * alone, alone - 0.85 * idle_us);
                 }
                 if (cost < best_cost) {
                     best_cost = cost;
@@ -918,7 +951,7 @@ int launch_repack(const float* src, float* dst, int planes, int H, int W, int Wp
 // persistent tile kernel.  src must have a pitch that is a multiple of 4 floats and a 16-byte aligned base.
 int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, int src_pitch, float* dst,
                            int dst_pitch, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s,
-                           cudaStream_t side) {
+                           SideLane* lane) {
     static int sm_counts[64] = {0};
     int sm_count = (dev >= 0 && dev < 64) ? sm_counts[dev] : 0;
     if (sm_count == 0) {
@@ -928,9 +961,9 @@ int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, cons
     if ((src_pitch & 3) != 0 || ((uintptr_t)src & 15) != 0)
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: source pitch/base not 16-byte aligned");
     const int Wt = tiling.Wt, Ht = tiling.Ht;
-    if (tiling.R == 8) return launch_one<8>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, side);
-    if (tiling.R == 9) return launch_one<9>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, side);
-    return launch_one<10>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, side);
+    if (tiling.R == 8) return launch_one<8>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, lane);
+    if (tiling.R == 9) return launch_one<9>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, lane);
+    return launch_one<10>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, lane);
 }
 
 }  // namespace pamr

@@ -15,13 +15,15 @@
 //    re-reading them through L1.  The next tile's weights are pulled into L2 with a bulk prefetch
 //    three classes before the tile boundary;
 //  * a producer warp streams the class planes of the tile (+24 px halo, 80 x (4R+48) floats)
-//    through an 8-slot shared-memory ring with TMA (cp.async.bulk.tensor.3d) + mbarriers; TMA
-//    zero-fills outside the image, so for border tiles the consuming group patches the halo in
-//    shared memory to replicate padding (pamr.py:50) before it computes;
+//    through a 4-slot shared-memory ring with TMA (cp.async.bulk.tensor.3d) + mbarriers; TMA
+//    zero-fills outside the image; replicate padding (pamr.py:50) in x is a per-lane clamped column
+//    offset, in y the consuming group patches the halo rows of top / bottom tiles before it computes;
 //  * FP32 math as packed FFMA2 over adjacent rows (a scalar FFMA with three distinct source
 //    registers issues only every ~1.8 cycles); results are stored with coalesced 128-byte rows; the
 //    per-(b,c) max for pseudo_gtmask is fused into the last iteration (warp reduce + atomicMax);
-//  * remainders of at most 8 columns / rows (W = H = 321) are computed by two small strip kernels.
+//  * remainders of at most 8 rows / columns (W = H = 321): the row strip is computed by the CTAs that
+//    are idle in the tile kernel's last wave (or a small launch when there are none), the column strip
+//    by a small kernel on a second stream, concurrently with the tile kernel.
 #include <cuda.h>
 
 #include <atomic>
@@ -630,11 +632,11 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(ctrl->tmem_base), "r"(512));
 }
 
-// ---- remainder strips as two small launches in front of the persistent kernel ----
-// (Alternatives measured on B200 and rejected: the same work inside the persistent kernel -- by the
-//  producer warp its ~100 global loads per item queue behind the compute warps' LDS traffic, by
-//  the compute warps at tile boundaries it lengthens every boundary; a concurrent side-stream
-//  launch does not co-reside with the persistent CTAs; partial tiles cost a whole tile column.)
+// ---- remainder strips as small kernels (row strip: only when the tile kernel's last wave has no idle CTAs) ----
+// (Alternatives measured on B200 and rejected: the same work inside the persistent kernel by the
+//  producer warp -- its ~100 global loads per item queue behind the compute warps' LDS traffic -- or by
+//  the compute warps at every tile boundary -- it lengthens every boundary; the remainder column fused
+//  into the last full tile column -- a bank-conflicted extra pass; partial tiles cost a whole tile column.)
 
 // Row strip: y in [Ht,H), all x.  One warp per 32 consecutive pixels of a row (coalesced).
 template <int R>

@@ -600,15 +600,24 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 for (int j = 0; j < CC; ++j) {
                     if (j < n) {
                         float* __restrict__ op = prm.dst + ((size_t)(b * C + c0 + j) * H + yw) * prm.dst_pitch + x;
-                        unsigned mx = 0u;
+                        const int nrow = xok ? min(R, H - yw) : 0;  // rows of this thread inside the image
+                        if (!(prm.exp_flags & 2)) {
+                            // running pointer: one 64-bit add per row instead of a 64-bit multiply-add chain
+                            const size_t pitch = (size_t)prm.dst_pitch;
+                            if (nrow == R) {
 #pragma unroll
-                        for (int i = 0; i < R; ++i) {
-                            if (xok && yw + i < H && !(prm.exp_flags & 2)) {
-                                op[(size_t)i * prm.dst_pitch] = acc[j][i];
-                                mx = max(mx, ordered_from_float(acc[j][i]));
+                                for (int i = 0; i < R; ++i, op += pitch) *op = acc[j][i];
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < R; ++i, op += pitch)
+                                    if (i < nrow) *op = acc[j][i];
                             }
                         }
-                        if (prm.cls_max != nullptr) {
+                        if (prm.cls_max != nullptr) {  // last iteration only: keep its ALU work out of the other nine
+                            unsigned mx = 0u;
+#pragma unroll
+                            for (int i = 0; i < R; ++i)
+                                if (i < nrow) mx = max(mx, ordered_from_float(acc[j][i]));
                             mx = __reduce_max_sync(0xffffffffu, mx);
                             if (lane == 0 && mx != 0u) atomicMax(prm.cls_max + (size_t)b * C + c0 + j, mx);
                         }

@@ -245,6 +245,43 @@ int pamr_pseudo_labels_f32(const float* m, const float* labels, const unsigned* 
                                 low_cut, cls_max_gated != 0, (cudaStream_t)stream);
 }
 
+size_t pamr_mask_ce_workspace_bytes(int B, int C, int H, int W) {
+    if (B < 1 || C < 1 || H < 1 || W < 1) return 0;
+    return mask_ce_workspace_bytes(B, C, H, W);
+}
+
+int pamr_labels_from_onehot_f32(const float* pseudo_gt, uint8_t* label, int* class_count, int B, int C, int H, int W,
+                                int dev, pamr_stream_t stream) {
+    PAMR_ENTER(dev);
+    PAMR_REQUIRE(pseudo_gt && label, "labels_from_onehot: NULL pointer");
+    PAMR_REQUIRE(C <= 255, "labels_from_onehot: C=%d does not fit a uint8 label map with 255 = ignore", C);
+    PAMR_TRY(check_dims(B, C, H, W));
+    return launch_labels_from_onehot(pseudo_gt, label, class_count, B, C, H, W, (cudaStream_t)stream);
+}
+
+int pamr_mask_ce_forward_f32(const float* logits, const uint8_t* label, const int* class_count, const float* gt_labels,
+                             float* loss, void* workspace, size_t workspace_bytes, int B, int C, int h, int w, int H,
+                             int W, int dev, pamr_stream_t stream) {
+    PAMR_ENTER(dev);
+    PAMR_REQUIRE(logits && label && class_count && gt_labels && loss, "mask_ce: NULL pointer");
+    PAMR_REQUIRE(h >= 1 && w >= 1, "mask_ce: non-positive dimension");
+    PAMR_REQUIRE(C >= 2 && C <= 255, "mask_ce: C=%d out of range", C);
+    PAMR_TRY(check_dims(B, C, H, W));
+    return launch_mask_ce_forward(logits, label, class_count, gt_labels, loss, workspace, workspace_bytes, B, C, h, w, H,
+                                  W, (cudaStream_t)stream);
+}
+
+int pamr_mask_ce_backward_f32(const float* logits, const uint8_t* label, const float* grad_loss, float* grad_logits,
+                              const void* workspace, size_t workspace_bytes, int B, int C, int h, int w, int H, int W,
+                              int dev, pamr_stream_t stream) {
+    PAMR_ENTER(dev);
+    PAMR_REQUIRE(logits && label && grad_loss && grad_logits, "mask_ce backward: NULL pointer");
+    PAMR_REQUIRE(h >= 1 && w >= 1, "mask_ce backward: non-positive dimension");
+    PAMR_TRY(check_dims(B, C, H, W));
+    return launch_mask_ce_backward(logits, label, grad_loss, grad_logits, workspace, workspace_bytes, B, C, h, w, H, W,
+                                   (cudaStream_t)stream);
+}
+
 int pamr_pseudo_labels_host_f32(const float* h_img, const float* h_mask, const float* h_labels, uint8_t* h_label, int B,
                                 int K, int C, int H, int W, int h, int w, const int* dilations, int nd, int iters,
                                 float bg_cut, float fg_cut, float low_cut, int dev) {

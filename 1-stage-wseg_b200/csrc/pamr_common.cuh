@@ -95,6 +95,34 @@ void count_launch(int n = 1);
         if (!(cond)) return ::pamr::set_error(PAMR_ERR_INVALID_ARGUMENT, __VA_ARGS__);           \
     } while (0)
 
+#ifdef __CUDACC__
+// torch's align_corners=True source index / weights (area_pixel_compute_scale,
+// guard_index_and_lambda), float arithmetic without FMA contraction.
+struct Lerp {
+    int i0, i1;
+    float l0, l1;
+};
+__device__ __forceinline__ Lerp make_lerp(int dst, float scale, int in_size) {
+    Lerp r;
+    const float f = __fmul_rn(scale, (float)dst);
+    r.i0 = min((int)f, in_size - 1);
+    r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+    r.l1 = fminf(fmaxf(__fsub_rn(f, (float)r.i0), 0.f), 1.f);
+    r.l0 = __fsub_rn(1.f, r.l1);
+    return r;
+}
+__device__ __forceinline__ float bilerp(const float* __restrict__ pl, int w, const Lerp& ly, const Lerp& lx) {
+    const float p00 = __ldg(pl + (size_t)ly.i0 * w + lx.i0), p01 = __ldg(pl + (size_t)ly.i0 * w + lx.i1);
+    const float p10 = __ldg(pl + (size_t)ly.i1 * w + lx.i0), p11 = __ldg(pl + (size_t)ly.i1 * w + lx.i1);
+    const float t0 = __fadd_rn(__fmul_rn(lx.l0, p00), __fmul_rn(lx.l1, p01));
+    const float t1 = __fadd_rn(__fmul_rn(lx.l0, p10), __fmul_rn(lx.l1, p11));
+    return __fadd_rn(__fmul_rn(ly.l0, t0), __fmul_rn(ly.l1, t1));
+}
+__host__ __device__ __forceinline__ float scale_of(int in_size, int out_size) {
+    return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+}
+#endif
+
 // Kernel launchers implemented in the .cu files (all enqueue on `s`, return a PAMR_* code).
 int launch_resize_bilinear(const float* src, float* dst, int n_planes, int h, int w, int H, int W, cudaStream_t s);
 int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, const Dilations& dil,
@@ -120,6 +148,15 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
                               int W, const Dilations& dil, int iters, unsigned* cls_max, int dev, cudaStream_t s);
 int launch_clean(const float* m, const float* labels, float* cleaned, unsigned* cls_max, int B, int C, int h, int w,
                  int H, int W, cudaStream_t s);
+// pamr_loss.cu (balanced_mask_loss_ce)
+size_t mask_ce_workspace_bytes(int B, int C, int H, int W);
+int launch_labels_from_onehot(const float* pseudo_gt, uint8_t* label, int* class_count, int B, int C, int H, int W,
+                              cudaStream_t s);
+int launch_mask_ce_forward(const float* logits, const uint8_t* label, const int* class_count, const float* gt_labels,
+                           float* loss, void* ws, size_t ws_bytes, int B, int C, int h, int w, int H, int W,
+                           cudaStream_t s);
+int launch_mask_ce_backward(const float* logits, const uint8_t* label, const float* grad_loss, float* grad_logits,
+                            const void* ws, size_t ws_bytes, int B, int C, int h, int w, int H, int W, cudaStream_t s);
 int launch_pseudo_labels(const float* m, const float* labels, const unsigned* cls_max, uint8_t* label,
                          float* pseudo_gt, int* class_count, int B, int C, int h, int w, int H, int W, float bg_cut,
                          float fg_cut, float low_cut, bool max_is_gated, cudaStream_t s);

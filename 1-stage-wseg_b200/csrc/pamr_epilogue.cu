@@ -13,32 +13,6 @@ namespace pamr {
 
 namespace {
 
-// torch's align_corners=True source index / weights (area_pixel_compute_scale,
-// guard_index_and_lambda), float arithmetic without FMA contraction.
-struct Lerp {
-    int i0, i1;
-    float l0, l1;
-};
-__device__ __forceinline__ Lerp make_lerp(int dst, float scale, int in_size) {
-    Lerp r;
-    const float f = __fmul_rn(scale, (float)dst);
-    r.i0 = min((int)f, in_size - 1);
-    r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
-    r.l1 = fminf(fmaxf(__fsub_rn(f, (float)r.i0), 0.f), 1.f);
-    r.l0 = __fsub_rn(1.f, r.l1);
-    return r;
-}
-__device__ __forceinline__ float bilerp(const float* __restrict__ pl, int w, const Lerp& ly, const Lerp& lx) {
-    const float p00 = __ldg(pl + (size_t)ly.i0 * w + lx.i0), p01 = __ldg(pl + (size_t)ly.i0 * w + lx.i1);
-    const float p10 = __ldg(pl + (size_t)ly.i1 * w + lx.i0), p11 = __ldg(pl + (size_t)ly.i1 * w + lx.i1);
-    const float t0 = __fadd_rn(__fmul_rn(lx.l0, p00), __fmul_rn(lx.l1, p01));
-    const float t1 = __fadd_rn(__fmul_rn(lx.l0, p10), __fmul_rn(lx.l1, p11));
-    return __fadd_rn(__fmul_rn(ly.l0, t0), __fmul_rn(ly.l1, t1));
-}
-__host__ __device__ __forceinline__ float scale_of(int in_size, int out_size) {
-    return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
-}
-
 constexpr int EP_BX = 32;
 constexpr int EP_BY = 8;
 

@@ -131,6 +131,35 @@ int pamr_pseudo_labels_f32(const float* m, const float* labels, const unsigned* 
                            pamr_stream_t stream);
 
 /*
+ * SURVEY 8(f) row 2 -- balanced_mask_loss_ce (models/SoftMaxAE.py:52-88), the direct consumer of the
+ * labels, and its gradient w.r.t. the mask logits.
+ *
+ * pamr_labels_from_onehot_f32: the reference passes pseudo_gt as a float one-hot-or-empty tensor
+ * [B,C,H,W]; this derives what the loss needs from it: label = argmax_c (first maximum), 255 where
+ * sum_c < 1 (SoftMaxAE.py:61-66), class_count[b,c] = pixels labelled c (:71-72).  Callers that hold the
+ * uint8 labels / counts of pamr_pseudo_labels_f32 skip this.
+ *
+ * pamr_mask_ce_forward_f32: logits [B,C,h,w] are interpolated on the fly (bilinear, align_corners=True,
+ * SoftMaxAE.py:58) to the label resolution [H,W];
+ *   cw[b,c] = (tot_b - n[b,c]) / (1 + tot_b)   bw[b] = (sum_c gt_labels[b,c] + 1 == #{c: n[b,c] > 0})
+ *   loss[b] = bw[b] * (1/(H*W)) * sum_px cw[b,label] * (logsumexp_c z - z[label])      (ignored pixels add 0)
+ * The workspace (pamr_mask_ce_workspace_bytes, 256-byte aligned) keeps per-pixel log-sum-exp and weights
+ * for the backward call.
+ *
+ * pamr_mask_ce_backward_f32: grad_logits [B,C,h,w] = d(sum_b grad_loss[b]*loss[b]) / d logits, from the
+ * same logits / label map and the workspace the forward call filled.  Deterministic (gather, no atomics).
+ */
+size_t pamr_mask_ce_workspace_bytes(int B, int C, int H, int W);
+int pamr_labels_from_onehot_f32(const float* pseudo_gt, uint8_t* label, int* class_count, int B, int C, int H, int W,
+                                int dev, pamr_stream_t stream);
+int pamr_mask_ce_forward_f32(const float* logits, const uint8_t* label, const int* class_count, const float* gt_labels,
+                             float* loss, void* workspace, size_t workspace_bytes, int B, int C, int h, int w, int H,
+                             int W, int dev, pamr_stream_t stream);
+int pamr_mask_ce_backward_f32(const float* logits, const uint8_t* label, const float* grad_loss, float* grad_logits,
+                              const void* workspace, size_t workspace_bytes, int B, int C, int h, int w, int H, int W,
+                              int dev, pamr_stream_t stream);
+
+/*
  * End-to-end convenience with HOST buffers (what a non-PyTorch caller binds): copies image, masks
  * and labels to the device, runs run_pamr (SoftMaxAE.py:176-179: image resized to the mask size,
  * PAMR) -> _rescale_and_clean -> pseudo_gtmask -> argmax, copies the uint8 label map back and

@@ -49,6 +49,7 @@ def lib():
         L.pamr_oracle_gate.argtypes = [_f, _f] + [ctypes.c_int] * 4
         L.pamr_oracle_pseudo_gt.argtypes = [_f, _f, _u8] + [ctypes.c_int] * 4 + [ctypes.c_float] * 3
         L.pamr_oracle_forward.argtypes = [_f, _f, _f] + [ctypes.c_int] * 7 + [_i, ctypes.c_int, ctypes.c_int]
+        L.pamr_oracle_mask_ce.argtypes = [_f, _f, _f, _f, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6
         _lib = L
     return _lib
 
@@ -174,3 +175,20 @@ def near_threshold_set(mask, tol=2e-5, **kw):
     """SURVEY 8(a) label-parity rule: pixels where some class is within tol of its threshold."""
     thr = thresholds(mask, **kw)
     return (np.abs(_c(mask) - thr[:, :, None, None]).min(1) <= tol)
+
+
+def balanced_mask_loss_ce(logits, pseudo_gt, gt_labels, gout=None):
+    """balanced_mask_loss_ce (SoftMaxAE.py:52-88): loss [B]; with gout [B] also the gradient of
+    sum_b gout[b]*loss[b] w.r.t. logits.  pseudo_gt is the float one-hot-or-empty tensor [B,C,H,W]."""
+    logits, pg, gl = _c(logits), _c(np.asarray(pseudo_gt, dtype=np.float32)), _c(gt_labels)
+    B, C, h, w = logits.shape
+    H, W = pg.shape[-2:]
+    loss = np.empty((B,), dtype=np.float32)
+    if gout is None:
+        lib().pamr_oracle_mask_ce(_p(logits), _p(pg), _p(gl), _p(loss), None, None, B, C, h, w, H, W)
+        return loss
+    gout = _c(gout)
+    grad = np.empty_like(logits)
+    lib().pamr_oracle_mask_ce(_p(logits), _p(pg), _p(gl), _p(loss), gout.ctypes.data_as(ctypes.c_void_p),
+                              grad.ctypes.data_as(ctypes.c_void_p), B, C, h, w, H, W)
+    return loss, grad

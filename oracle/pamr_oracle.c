@@ -283,3 +283,101 @@ void pamr_oracle_forward(const float* img, const float* mask, float* out, int B,
     free(aff);
     free(m0);
 }
+
+/*
+ * balanced_mask_loss_ce (models/SoftMaxAE.py:52-88) and its gradient w.r.t. `mask`.
+ *   z = bilinear(mask -> size of pseudo_gt), align_corners=True                      (:58)
+ *   label = argmax_c pseudo_gt, ignored where sum_c pseudo_gt < 1                    (:61-66)
+ *   n[b,c] = sum_px pseudo_gt, tot = sum_c n, cw[b,c] = (tot - n)/(1 + tot) (float)   (:71-74)
+ *   ce(px) = logsumexp_c z - z[label]  (0 at ignored pixels)                        (:77)
+ *   bw[b] = (sum gt_labels + 1 == #{c : n[b,c] > 0})                                (:82-84)
+ *   loss[b] = bw[b] * mean_px(cw[b,label] * ce)   (mean over ALL H*W pixels)         (:86)
+ * Gradient of sum_b gout[b]*loss[b]:  dz_c(px) = gout*bw*cw[label]/(H*W) * (softmax_c - [c == label]),
+ * pushed through the transpose of the bilinear interpolation.  Sums are accumulated in double.
+ * logits [B,C,h,w], pg [B,C,H,W] float one-hot-or-empty, gt_labels [B,C-1], loss [B];
+ * gout [B] and grad [B,C,h,w] may both be NULL.
+ */
+void pamr_oracle_mask_ce(const float* logits, const float* pg, const float* gt_labels, float* loss,
+                         const float* gout, float* grad, int B, int C, int h, int w, int H, int W) {
+    const size_t HW = (size_t)H * W, hw = (size_t)h * w;
+    const float sh = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+    const float sw = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    const int same = (h == H && w == W);
+    for (int b = 0; b < B; ++b) {
+        float* cw = (float*)malloc(sizeof(float) * C);
+        double* gacc = grad ? (double*)calloc((size_t)C * hw, sizeof(double)) : NULL;
+        double* z = (double*)malloc(sizeof(double) * C);
+        float tot = 0.f;
+        int present = 0;
+        for (int c = 0; c < C; ++c) {
+            double s = 0.0;
+            for (size_t i = 0; i < HW; ++i) s += pg[((size_t)b * C + c) * HW + i];
+            cw[c] = (float)s;  /* n[b,c], an integer */
+            tot += (float)s;
+            present += s > 0.0;
+        }
+        for (int c = 0; c < C; ++c) cw[c] = (tot - cw[c]) / (1.f + tot);
+        float gsum = 1.f;  /* + BG */
+        for (int c = 0; c < C - 1; ++c) gsum += gt_labels[(size_t)b * (C - 1) + c];
+        const float bw = (gsum == (float)present) ? 1.f : 0.f;
+        double acc = 0.0;
+        for (int y = 0; y < H; ++y) {
+            const float fy = sh * (float)y;
+            int y0 = (int)fy;
+            if (y0 > h - 1) y0 = h - 1;
+            const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+            const float ly1 = fy - (float)y0, ly0 = 1.f - ly1;
+            for (int x = 0; x < W; ++x) {
+                const size_t i = (size_t)y * W + x;
+                int label = -1;
+                float best = 0.f, sum = 0.f;
+                for (int c = 0; c < C; ++c) {
+                    const float v = pg[((size_t)b * C + c) * HW + i];
+                    sum += v;
+                    if (label < 0 || v > best) { best = v; label = c; }  /* first maximum, like torch.argmax */
+                }
+                if (sum < 1.f) continue;  /* ignored: contributes 0 to the sum, still counted in the mean */
+                const float fx = sw * (float)x;
+                int x0 = (int)fx;
+                if (x0 > w - 1) x0 = w - 1;
+                const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+                const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+                double m = -1e300;
+                for (int c = 0; c < C; ++c) {
+                    const float* pl = logits + ((size_t)b * C + c) * hw;
+                    const float v = same ? pl[i]
+                                         : ly0 * (lx0 * pl[(size_t)y0 * w + x0] + lx1 * pl[(size_t)y0 * w + x1]) +
+                                               ly1 * (lx0 * pl[(size_t)y1 * w + x0] + lx1 * pl[(size_t)y1 * w + x1]);
+                    z[c] = (double)v;
+                    if (z[c] > m) m = z[c];
+                }
+                double se = 0.0;
+                for (int c = 0; c < C; ++c) se += exp(z[c] - m);
+                const double lse = m + log(se);
+                acc += (double)cw[label] * (lse - z[label]);
+                if (gacc) {
+                    const double k = (double)gout[b] * bw * cw[label] / (double)HW;
+                    for (int c = 0; c < C; ++c) {
+                        const double d = k * (exp(z[c] - lse) - (c == label ? 1.0 : 0.0));
+                        double* ga = gacc + (size_t)c * hw;
+                        if (same) {
+                            ga[i] += d;
+                        } else {
+                            ga[(size_t)y0 * w + x0] += d * ly0 * lx0;
+                            ga[(size_t)y0 * w + x1] += d * ly0 * lx1;
+                            ga[(size_t)y1 * w + x0] += d * ly1 * lx0;
+                            ga[(size_t)y1 * w + x1] += d * ly1 * lx1;
+                        }
+                    }
+                }
+            }
+        }
+        loss[b] = bw * (float)(acc / (double)HW);
+        if (gacc) {
+            for (size_t e = 0; e < (size_t)C * hw; ++e) grad[(size_t)b * C * hw + e] = (float)gacc[e];
+            free(gacc);
+        }
+        free(cw);
+        free(z);
+    }
+}

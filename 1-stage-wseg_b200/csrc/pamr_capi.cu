@@ -245,6 +245,18 @@ int pamr_pseudo_labels_f32(const float* m, const float* labels, const unsigned* 
                                 low_cut, cls_max_gated != 0, (cudaStream_t)stream);
 }
 
+int pamr_merge_multiscale_f32(const float* masks, const int* pads_host, const float* labels, float* merged,
+                              uint8_t* pred, int S, int C, int Hp, int Wp, int H, int W, int flip, float bg_pow,
+                              float prospect_thresh, int dev, pamr_stream_t stream) {
+    PAMR_ENTER(dev);
+    PAMR_REQUIRE(masks && pads_host && (merged || pred), "merge: NULL pointer");
+    PAMR_REQUIRE(C >= 1 && C <= 255, "merge: C=%d does not fit a uint8 prediction", C);
+    PAMR_REQUIRE(Hp >= 1 && Wp >= 1, "merge: non-positive dimension");
+    PAMR_TRY(check_dims(1, C, H, W));
+    return launch_merge_multiscale(masks, pads_host, labels, merged, pred, S, C, Hp, Wp, H, W, flip, bg_pow,
+                                   prospect_thresh, (cudaStream_t)stream);
+}
+
 size_t pamr_mask_ce_workspace_bytes(int B, int C, int H, int W) {
     if (B < 1 || C < 1 || H < 1 || W < 1) return 0;
     return mask_ce_workspace_bytes(B, C, H, W);

@@ -119,6 +119,54 @@ pseudo_labels_kernel(const float* __restrict__ m, const float* __restrict__ labe
     }
 }
 
+// ---- multi-scale merge + prediction (utils/inference_tools.py:134-161, :85-88) ----
+// torch's align_corners=False source index: src = max(0, (in/out)*(dst + 0.5) - 0.5)
+__device__ __forceinline__ Lerp make_lerp_half_pixel(int dst, int in_size, int out_size) {
+    Lerp r;
+    const float scale = __fdiv_rn((float)in_size, (float)out_size);
+    const float f = fmaxf(__fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f), 0.f);
+    r.i0 = min((int)f, in_size - 1);
+    r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+    r.l1 = __fsub_rn(f, (float)r.i0);
+    r.l0 = __fsub_rn(1.f, r.l1);
+    return r;
+}
+
+constexpr int MERGE_MAX_S = 16;
+struct MergePads {
+    int v[MERGE_MAX_S][4];  // pad_t, pad_l, h_s, w_s
+};
+
+// One thread per output pixel, all classes: mean over the scales of the un-padded, resized, un-flipped,
+// label-gated score, BG ** bg_pow, then fg < thresh -> 0 and argmax (first maximum).  grid (tiles_x, tiles_y)
+__global__ void __launch_bounds__(EP_BX * EP_BY)
+merge_multiscale_kernel(const float* __restrict__ masks, const MergePads pads, const float* __restrict__ labels,
+                        float* __restrict__ merged, uint8_t* __restrict__ pred, int S, int C, int Hp, int Wp, int H, int W,
+                        int flip, float bg_pow, float thresh) {
+    const int x = blockIdx.x * EP_BX + threadIdx.x, y = blockIdx.y * EP_BY + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t plane = (size_t)Hp * Wp;
+    int arg = 0;
+    float best = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float gate = (c > 0 && labels != nullptr) ? __ldg(labels + c - 1) : 1.f;
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) {
+            const int xs = (flip && (s & 1)) ? W - 1 - x : x;
+            const Lerp ly = make_lerp_half_pixel(y, pads.v[s][2], H), lx = make_lerp_half_pixel(xs, pads.v[s][3], W);
+            float v = bilerp(masks + ((size_t)s * C + c) * plane + (size_t)pads.v[s][0] * Wp + pads.v[s][1], Wp, ly, lx);
+            if (c > 0 && labels != nullptr) v = __fmul_rn(v, gate);
+            acc = __fadd_rn(acc, v);
+        }
+        float m = __fdiv_rn(acc, (float)S);
+        if (c == 0) m = powf(m, bg_pow);
+        if (merged != nullptr) merged[((size_t)c * H + y) * W + x] = m;
+        const float t = (c > 0 && m < thresh) ? 0.f : m;
+        if (c == 0 || t > best) { best = t; arg = c; }
+    }
+    if (pred != nullptr) pred[(size_t)y * W + x] = (uint8_t)arg;
+}
+
 }  // namespace
 
 int launch_resize_bilinear(const float* src, float* dst, int n_planes, int h, int w, int H, int W, cudaStream_t s) {
@@ -179,4 +227,25 @@ int launch_pseudo_labels(const float* m, const float* labels, const unsigned* cl
     return PAMR_OK;
 }
 
+}  // namespace pamr
+
+namespace pamr {
+int launch_merge_multiscale(const float* masks, const int* pads_host, const float* labels, float* merged, uint8_t* pred,
+                            int S, int C, int Hp, int Wp, int H, int W, int flip, float bg_pow, float thresh,
+                            cudaStream_t s) {
+    if (S < 1 || S > MERGE_MAX_S) return set_error(PAMR_ERR_INVALID_ARGUMENT, "merge: 1..%d scales supported, got %d", MERGE_MAX_S, S);
+    MergePads pads;
+    for (int i = 0; i < S; ++i) {
+        for (int k = 0; k < 4; ++k) pads.v[i][k] = pads_host[4 * i + k];
+        const int pt = pads.v[i][0], pl = pads.v[i][1], hs = pads.v[i][2], ws = pads.v[i][3];
+        if (pt < 0 || pl < 0 || hs < 1 || ws < 1 || pt + hs > Hp || pl + ws > Wp)
+            return set_error(PAMR_ERR_INVALID_ARGUMENT, "merge: pads[%d] = (%d,%d,%d,%d) outside the %dx%d mask", i, pt, pl, hs, ws, Hp, Wp);
+    }
+    dim3 grid((W + EP_BX - 1) / EP_BX, (H + EP_BY - 1) / EP_BY), block(EP_BX, EP_BY);
+    if (grid.y > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "merge: H/8 must be <= 65535");
+    merge_multiscale_kernel<<<grid, block, 0, s>>>(masks, pads, labels, merged, pred, S, C, Hp, Wp, H, W, flip, bg_pow, thresh);
+    count_launch();
+    PAMR_CUDA_TRY(cudaGetLastError());
+    return PAMR_OK;
+}
 }  // namespace pamr

@@ -160,6 +160,20 @@ int pamr_mask_ce_backward_f32(const float* logits, const uint8_t* label, const f
                               int dev, pamr_stream_t stream);
 
 /*
+ * SURVEY 8(f) row 3 -- inference post-processing, one image:
+ *   MergeMultiScale._merge_masks (utils/inference_tools.py:134-161): every scale s of masks [S,C,Hp,Wp] is
+ *   un-padded (pads[s] = pad_t, pad_l, h_s, w_s; HOST array of 4*S ints), resized to [H,W] (bilinear,
+ *   align_corners=False), flipped back along x for odd s when flip != 0, its foreground classes gated by
+ *   labels [C-1] (device, or NULL); the scales are averaged and the background raised to bg_pow;
+ *   ResultWriter.save, no-CRF path (:85-88): foreground scores < prospect_thresh are zeroed, pred = argmax.
+ * merged: NULL or float [C,H,W];  pred: NULL or uint8 [H,W].  S <= 16.
+ * (The reference moves the [S,C,Hp,Wp] scores to the host for this; here only the uint8 map has to.)
+ */
+int pamr_merge_multiscale_f32(const float* masks, const int* pads_host, const float* labels, float* merged,
+                              uint8_t* pred, int S, int C, int Hp, int Wp, int H, int W, int flip, float bg_pow,
+                              float prospect_thresh, int dev, pamr_stream_t stream);
+
+/*
  * End-to-end convenience with HOST buffers (what a non-PyTorch caller binds): copies image, masks
  * and labels to the device, runs run_pamr (SoftMaxAE.py:176-179: image resized to the mask size,
  * PAMR) -> _rescale_and_clean -> pseudo_gtmask -> argmax, copies the uint8 label map back and

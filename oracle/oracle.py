@@ -49,6 +49,8 @@ def lib():
         L.pamr_oracle_gate.argtypes = [_f, _f] + [ctypes.c_int] * 4
         L.pamr_oracle_pseudo_gt.argtypes = [_f, _f, _u8] + [ctypes.c_int] * 4 + [ctypes.c_float] * 3
         L.pamr_oracle_forward.argtypes = [_f, _f, _f] + [ctypes.c_int] * 7 + [_i, ctypes.c_int, ctypes.c_int]
+        L.pamr_oracle_merge_multiscale.argtypes = [_f, _i, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p] + \
+            [ctypes.c_int] * 7 + [ctypes.c_float] * 2
         L.pamr_oracle_mask_ce.argtypes = [_f, _f, _f, _f, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 6
         _lib = L
     return _lib
@@ -192,3 +194,19 @@ def balanced_mask_loss_ce(logits, pseudo_gt, gt_labels, gout=None):
     lib().pamr_oracle_mask_ce(_p(logits), _p(pg), _p(gl), _p(loss), gout.ctypes.data_as(ctypes.c_void_p),
                               grad.ctypes.data_as(ctypes.c_void_p), B, C, h, w, H, W)
     return loss, grad
+
+
+def merge_multiscale(masks, pads, labels, imsize_hw, flip, bg_pow, prospect_thresh):
+    """MergeMultiScale._merge_masks (utils/inference_tools.py:134-161) + the no-CRF prediction of
+    ResultWriter.save (:85-88): returns (merged [C,H,W] float32, pred [H,W] uint8)."""
+    masks = _c(masks)
+    S, C, Hp, Wp = masks.shape
+    H, W = int(imsize_hw[0]), int(imsize_hw[1])
+    pads = np.ascontiguousarray(pads, dtype=np.int32)
+    lab = None if labels is None else _c(labels)
+    merged = np.empty((C, H, W), dtype=np.float32)
+    pred = np.empty((H, W), dtype=np.uint8)
+    lib().pamr_oracle_merge_multiscale(_p(masks), pads.ctypes.data_as(_i), None if lab is None else lab.ctypes.data_as(ctypes.c_void_p),
+                                       merged.ctypes.data_as(ctypes.c_void_p), pred.ctypes.data_as(ctypes.c_void_p), S, C, Hp, Wp,
+                                       H, W, int(bool(flip)), float(bg_pow), float(prospect_thresh))
+    return merged, pred

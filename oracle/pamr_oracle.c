@@ -381,3 +381,69 @@ void pamr_oracle_mask_ce(const float* logits, const float* pg, const float* gt_l
         free(z);
     }
 }
+
+/*
+ * inference post-processing.
+ * MergeMultiScale._merge_masks (utils/inference_tools.py:134-161): for every scale s
+ *   cut   masks[s][:, pad_t:pad_t+h_s, pad_l:pad_l+w_s]                      (:136-138, :143)
+ *   F.interpolate(cut, (H,W), bilinear, align_corners=False)                 (:146)
+ *   flipped back along x for odd s when FLIP                                 (:149-150)
+ *   foreground classes multiplied by the image-level labels                  (:154)
+ * then the mean over the scales (sequential float sum / S, :158) and mean[0] = mean[0] ** BG_POW (:162).
+ * ResultWriter.save, no-CRF path (:85-88): foreground scores < prospect_thresh are zeroed, pred = argmax.
+ * torch's align_corners=False source index: src = max(0, (in/out)*(dst + 0.5) - 0.5).
+ * masks [S,C,Hp,Wp], pads [S,4] = (pad_t, pad_l, h_s, w_s), labels [C-1] or NULL;
+ * merged [C,H,W] (may be NULL), pred [H,W] uint8 (may be NULL).
+ */
+static inline void lerp_half_pixel(int dst, int in_size, int out_size, int* i0, int* i1, float* l0, float* l1) {
+    const float scale = (float)in_size / (float)out_size;
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    int a = (int)src;
+    if (a > in_size - 1) a = in_size - 1;
+    *i0 = a;
+    *i1 = a + (a < in_size - 1 ? 1 : 0);
+    *l1 = src - (float)a;
+    *l0 = 1.f - *l1;
+}
+
+void pamr_oracle_merge_multiscale(const float* masks, const int* pads, const float* labels, float* merged,
+                                  uint8_t* pred, int S, int C, int Hp, int Wp, int H, int W, int flip,
+                                  float bg_pow, float prospect_thresh) {
+    float* mean = (float*)malloc(sizeof(float) * (size_t)C * H * W);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int c = 0; c < C; ++c)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                float acc = 0.f;
+                for (int s = 0; s < S; ++s) {
+                    const int pt = pads[4 * s], pl = pads[4 * s + 1], hs = pads[4 * s + 2], ws = pads[4 * s + 3];
+                    const int xs = (flip && (s & 1)) ? W - 1 - x : x;
+                    int y0, y1, x0, x1;
+                    float ly0, ly1, lx0, lx1;
+                    lerp_half_pixel(y, hs, H, &y0, &y1, &ly0, &ly1);
+                    lerp_half_pixel(xs, ws, W, &x0, &x1, &lx0, &lx1);
+                    const float* pl_ = masks + (((size_t)s * C + c) * Hp + pt) * Wp + pl;
+                    float v = ly0 * (lx0 * pl_[(size_t)y0 * Wp + x0] + lx1 * pl_[(size_t)y0 * Wp + x1]) +
+                              ly1 * (lx0 * pl_[(size_t)y1 * Wp + x0] + lx1 * pl_[(size_t)y1 * Wp + x1]);
+                    if (c > 0 && labels) v *= labels[c - 1];
+                    acc += v;
+                }
+                float m = acc / (float)S;
+                if (c == 0) m = powf(m, bg_pow);
+                mean[((size_t)c * H + y) * W + x] = m;
+            }
+    if (merged) memcpy(merged, mean, sizeof(float) * (size_t)C * H * W);
+    if (pred)
+        for (size_t i = 0; i < (size_t)H * W; ++i) {
+            int arg = 0;
+            float best = mean[i];
+            for (int c = 1; c < C; ++c) {
+                float v = mean[(size_t)c * H * W + i];
+                if (v < prospect_thresh) v = 0.f;
+                if (v > best) { best = v; arg = c; }
+            }
+            pred[i] = (uint8_t)arg;
+        }
+    free(mean);
+}

@@ -70,6 +70,8 @@ def lib():
                         "(there is no CPU or PyTorch fallback)" % (LIB_PATH, CSRC))
                 L = ctypes.CDLL(LIB_PATH)
                 for name, (res, args) in SIGNATURES.items():
+                    if not hasattr(L, name) and os.environ.get("PAMR_B200_OLD_LIBRARY") == "1":
+                        continue  # A/B experiments against a library built from an older commit (tools/build_variant.sh)
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args

@@ -8,6 +8,8 @@
 // one thread per pixel, neighbours fetched through L1 with clamped coordinates) and the STRIP
 // (the few remainder columns / rows the tuned kernel's tiles leave out are computed inside the tuned launch).  The tuned sm_100a
 // kernel for the standard dilation set lives in pamr_propagate_sm100.cu.
+#include <cstdlib>
+
 #include "pamr_common.cuh"
 
 namespace pamr {
@@ -205,7 +207,9 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: tiled affinity without the tuned kernel");
     const bool need_repack = tuned && ((W & 3) != 0 || ((uintptr_t)m_in & 15) != 0);
 
-    const bool col_strip = tuned && tiling.Wt < W;  // runs on the side stream, concurrently with the tiles
+    // the column strip runs on the side stream, concurrently with the tiles (PAMR_B200_NO_LANE=1: serialised)
+    static const bool no_lane = getenv("PAMR_B200_NO_LANE") != nullptr;
+    const bool col_strip = tuned && tiling.Wt < W && !no_lane;
     ForkJoin fj;
     if (need_repack || col_strip) {
         int rc = fj.init(dev, s);

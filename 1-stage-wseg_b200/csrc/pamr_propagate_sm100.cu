@@ -44,6 +44,15 @@ constexpr int NW = 4;                 // warps per compute group (= TMEM lane qu
 constexpr int NG = 3;                 // compute groups that share the tile's weights in TMEM (class c -> group c % NG)
 constexpr int NWC = NG * NW;          // compute warps
 constexpr int NSLOT = 4;              // class-plane slots in the shared-memory ring
+// mbarriers of the ring: sequence number n uses slot n % NSLOT but barrier pair n % NBAR.  Waits are by
+// phase PARITY, which is only sound if a waiter can never be a whole phase ahead of the barrier.  With one
+// barrier per slot and 4 slots, a group that has finished class k-3 tests the barrier of class k while the
+// load of class k-4 (same slot, other group) may -- once in ~1e7 passes, when that load straggles -- still
+// be in flight; the parity test then reports the OLD phase as "complete" and the group computes on the wrong
+// plane (measured: 0.2-2.5 % of the forward calls had one wrong tile-class; 0 of 2500 with 8 slots).  Eight
+// barrier pairs put 8 sequence numbers between two uses of a barrier, as in the 8-slot ring.
+constexpr int NBAR = 8;
+static_assert(NBAR % NSLOT == 0 && NBAR >= 2 * NSLOT, "barrier ring must cover at least two uses of every slot");
 #ifndef PAMR_CC
 #define PAMR_CC 1
 #endif
@@ -133,8 +142,8 @@ struct Cfg {
 };
 
 struct Ctrl {  // lives in the last 1 KB of dynamic shared memory
-    unsigned long long tma_bar[NSLOT];
-    unsigned long long empty_bar[NSLOT];
+    unsigned long long tma_bar[NBAR];
+    unsigned long long empty_bar[NBAR];
     uint32_t tmem_base;
 };
 
@@ -439,7 +448,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
     const int C = prm.C, H = prm.H, W = prm.W;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSLOT; ++s) {
+        for (int s = 0; s < NBAR; ++s) {
             mbar_init(smem_u32(&ctrl->tma_bar[s]), 1);
             mbar_init(smem_u32(&ctrl->empty_bar[s]), NW);  // the NW warps of the group that read the slot
         }
@@ -458,21 +467,24 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
 
     if (warp == NWC) {
         // ===================== producer warp: TMA issue =====================
-        // Sequence number n = (tile_iter, class) -> slot n % NSLOT.  A consumer group waits for
-        // tma_bar (bytes landed), patches the halo itself if the tile touches the image border,
-        // computes, and releases the slot through empty_bar.
+        // Sequence number n = (tile_iter, class) -> slot n % NSLOT, barrier pair n % NBAR.  A consumer
+        // group waits for tma_bar (bytes landed), patches the halo itself if the tile touches the image
+        // border, computes, and releases the slot through empty_bar; the producer may refill slot
+        // n % NSLOT once sequence number n - NSLOT has been released.
         const long long total = (long long)my_tiles * C;
         int pn = 0;
         for (long long n_issue = 0; n_issue < total; ++n_issue) {
-            const int s = (int)(n_issue % NSLOT);
-            const uint32_t round = (uint32_t)(n_issue / NSLOT);
+            const int s = (int)(n_issue % NSLOT), bi = (int)(n_issue % NBAR);
             const int ti = (int)(n_issue / C), c = (int)(n_issue % C);
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
             const int x0 = (t % prm.tiles_x) * TX, y0 = (t / prm.tiles_x) * C_::TY;
-            if (lane == 0) mbar_wait_sleep(smem_u32(&ctrl->empty_bar[s]), (round & 1u) ^ 1u);
+            if (lane == 0 && n_issue >= NSLOT) {  // the previous occupant of this slot has been consumed
+                const long long prev = n_issue - NSLOT;
+                mbar_wait_sleep(smem_u32(&ctrl->empty_bar[prev % NBAR]), (uint32_t)(prev / NBAR) & 1u);
+            }
             if (lane == 0) {
-                const uint32_t bar = smem_u32(&ctrl->tma_bar[s]);
+                const uint32_t bar = smem_u32(&ctrl->tma_bar[bi]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive_expect_tx(bar, C_::SLOT_BYTES);
                 tma_load_3d(smem_u32(slots + (size_t)s * C_::SLOT_FLOATS), &tmap, bar, x0 - HALO, y0 - HALO, b * C + c);
@@ -558,10 +570,10 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             for (int k = grp; k < C; k += NG) {
                 const int c0 = k, n = 1;
                 const long long sq = seq0 + k;
-                const int s = (int)(sq % NSLOT);
-                const uint32_t par = (uint32_t)(sq / NSLOT) & 1u;
+                const int s = (int)(sq % NSLOT), bi = (int)(sq % NBAR);
+                const uint32_t par = (uint32_t)(sq / NBAR) & 1u;
                 PAMR_EV(100 + k);
-                if (!probe && !(prm.exp_flags & 8)) mbar_wait_sleep(smem_u32(&ctrl->tma_bar[s]), par);  // bytes landed
+                if (!probe && !(prm.exp_flags & 8)) mbar_wait_sleep(smem_u32(&ctrl->tma_bar[bi]), par);  // bytes landed
                 if (border && !(prm.exp_flags & 4)) {  // replicate padding: the group patches the halo of its own slot
                     patch_window<R>(slots + (size_t)s * C_::SLOT_FLOATS, x0, y0, H, W, wq, lane);
                     // immediate barrier ids: with a register id ptxas reserves all 16 named barriers and no
@@ -584,16 +596,15 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 PAMR_EV(9);
                 // release the slot as early as possible
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&ctrl->empty_bar[s]));
+                if (lane == 0) mbar_arrive(smem_u32(&ctrl->empty_bar[bi]));
                 // Probe the next class's barriers now, without blocking: an mbarrier test takes a few
                 // hundred cycles when the LSU queues are full of LDS, and that latency then overlaps the
                 // stores below instead of sitting at the head of the next pass.
                 probe = 0;
                 if (k + NG < C) {
                     const long long sq2 = sq + NG;
-                    const int s2 = (int)(sq2 % NSLOT);
-                    const uint32_t par2 = (uint32_t)(sq2 / NSLOT) & 1u;
-                    probe = (int)mbar_poll(smem_u32(&ctrl->tma_bar[s2]), par2);
+                    const uint32_t par2 = (uint32_t)(sq2 / NBAR) & 1u;
+                    probe = (int)mbar_poll(smem_u32(&ctrl->tma_bar[sq2 % NBAR]), par2);
                 }
                 PAMR_EV(7);
                 // ---- store (coalesced 128 B per row) and optional class max

@@ -375,3 +375,20 @@ def test_host_pipeline_matches_device_path():
     d_out = torch.empty((B, H, W), dtype=torch.uint8, device=DEV)
     pipe(pin(image), pin(masks), pin(labels), d_out=d_out)
     np.testing.assert_array_equal(N(d_out), ref)
+
+
+def test_repeatability_under_allocator_churn():
+    """Race detector for the tile kernel's TMA / mbarrier ring: the same forward, repeated with
+    unrelated allocations in between, must be bit-identical every time.  (A ring whose parity waits
+    could alias -- 4 barrier pairs for 4 slots -- produced one wrong tile-class in 0.2-2.5 % of the
+    calls at this shape; with 8 barrier pairs 0 of 5500.)"""
+    B, C, H, W = 16, 21, 320, 320
+    image = G(synth.image_uniform(B, 3, H, W, 51))
+    mask = G(synth.mask_softmax(B, C, H, W, 52))
+    pamr = wseg_b200.PAMR(10, D6).to(DEV)
+    ref = pamr(image, mask).clone()
+    bad = 0
+    for _ in range(400):
+        junk = torch.rand((B, C, H, W), device=DEV)  # noqa: F841  (L2 / allocator churn)
+        bad += int(not torch.equal(pamr(image, mask), ref))
+    assert bad == 0

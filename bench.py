@@ -97,6 +97,11 @@ def cpu_baseline_sample(steps, warmup):
     img = synth.image_uniform(1, K_IMG, H_IMG, W_IMG, 0)
     msk = synth.mask_softmax(1, C_CLS, H_IMG, W_IMG, 1)
     lab = synth.labels_bernoulli(1, C_CLS, 2, p=0.3)
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    try:
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        oracle.set_num_threads(os.cpu_count() or 1)
     cores = oracle.num_threads()
 
     def step():

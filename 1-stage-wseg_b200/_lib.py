@@ -35,6 +35,7 @@ SIGNATURES = {
     "pamr_clean_f32": (_i, [_vp, _vp, _vp, _vp] + [_i] * 6 + [_i, _vp]),
     "pamr_pseudo_labels_f32": (_i, [_vp] * 6 + [_i] * 6 + [_f, _f, _f, _i, _i, _vp]),
     "pamr_pseudo_labels_host_f32": (_i, [_vp] * 4 + [_i] * 7 + [_vp, _i, _i, _f, _f, _f, _i]),
+    "pamr_denorm_resize_f32": (_i, [_vp] * 4 + [_i] * 6 + [_i, _vp]),
     "pamr_merge_multiscale_f32": (_i, [_vp] * 5 + [_i] * 7 + [_f, _f, _i, _vp]),
     "pamr_mask_ce_workspace_bytes": (ctypes.c_size_t, [_i] * 4),
     "pamr_labels_from_onehot_f32": (_i, [_vp, _vp, _vp] + [_i] * 4 + [_i, _vp]),

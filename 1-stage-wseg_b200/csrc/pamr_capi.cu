@@ -245,6 +245,15 @@ int pamr_pseudo_labels_f32(const float* m, const float* labels, const unsigned* 
                                 low_cut, cls_max_gated != 0, (cudaStream_t)stream);
 }
 
+int pamr_denorm_resize_f32(const float* img_norm, const float* mean_host, const float* std_host, float* dst, int B,
+                           int K, int h, int w, int H, int W, int dev, pamr_stream_t stream) {
+    PAMR_ENTER(dev);
+    PAMR_REQUIRE(img_norm && mean_host && std_host && dst, "denorm: NULL pointer");
+    PAMR_REQUIRE(h >= 1 && w >= 1, "denorm: non-positive dimension");
+    PAMR_TRY(check_dims(B, K, H, W));
+    return launch_denorm_resize(img_norm, dst, mean_host, std_host, B, K, h, w, H, W, (cudaStream_t)stream);
+}
+
 int pamr_merge_multiscale_f32(const float* masks, const int* pads_host, const float* labels, float* merged,
                               uint8_t* pred, int S, int C, int Hp, int Wp, int H, int W, int flip, float bg_pow,
                               float prospect_thresh, int dev, pamr_stream_t stream) {

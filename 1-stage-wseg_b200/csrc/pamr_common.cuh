@@ -148,6 +148,8 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
                               int W, const Dilations& dil, int iters, unsigned* cls_max, int dev, cudaStream_t s);
 int launch_clean(const float* m, const float* labels, float* cleaned, unsigned* cls_max, int B, int C, int h, int w,
                  int H, int W, cudaStream_t s);
+int launch_denorm_resize(const float* src, float* dst, const float* mean_host, const float* std_host, int B, int K, int h,
+                         int w, int H, int W, cudaStream_t s);
 int launch_merge_multiscale(const float* masks, const int* pads_host, const float* labels, float* merged, uint8_t* pred,
                             int S, int C, int Hp, int Wp, int H, int W, int flip, float bg_pow, float thresh,
                             cudaStream_t s);

@@ -119,6 +119,38 @@ pseudo_labels_kernel(const float* __restrict__ m, const float* __restrict__ labe
     }
 }
 
+// ---- the data set's denorm (datasets/pascal_voc.py:85-101, called at train.py:120) folded
+// into the image down-sampling of run_pamr (SoftMaxAE.py:177): raw = norm * std[k] + mean[k] (two roundings,
+// as t.mul_(s).add_(m) does), evaluated on the four source pixels, then the bilinear expression.
+struct ChannelAffine {
+    float scale[8], shift[8];
+};
+template <bool kResize>
+__global__ void __launch_bounds__(EP_BX * EP_BY)
+denorm_resize_kernel(const float* __restrict__ src, float* __restrict__ dst, const ChannelAffine aff, int K, int h, int w,
+                     int H, int W, float sh, float sw) {
+    const int x = blockIdx.x * EP_BX + threadIdx.x;
+    const int y = blockIdx.y * EP_BY + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t n = blockIdx.z;
+    const float sc = aff.scale[n % K], sf = aff.shift[n % K];
+    const float* __restrict__ pl = src + n * h * w;
+    float v;
+    if (kResize) {
+        const Lerp ly = make_lerp(y, sh, h), lx = make_lerp(x, sw, w);
+        const float p00 = __fadd_rn(__fmul_rn(__ldg(pl + (size_t)ly.i0 * w + lx.i0), sc), sf);
+        const float p01 = __fadd_rn(__fmul_rn(__ldg(pl + (size_t)ly.i0 * w + lx.i1), sc), sf);
+        const float p10 = __fadd_rn(__fmul_rn(__ldg(pl + (size_t)ly.i1 * w + lx.i0), sc), sf);
+        const float p11 = __fadd_rn(__fmul_rn(__ldg(pl + (size_t)ly.i1 * w + lx.i1), sc), sf);
+        const float t0 = __fadd_rn(__fmul_rn(lx.l0, p00), __fmul_rn(lx.l1, p01));
+        const float t1 = __fadd_rn(__fmul_rn(lx.l0, p10), __fmul_rn(lx.l1, p11));
+        v = __fadd_rn(__fmul_rn(ly.l0, t0), __fmul_rn(ly.l1, t1));
+    } else {
+        v = __fadd_rn(__fmul_rn(__ldg(pl + (size_t)y * w + x), sc), sf);
+    }
+    dst[(n * H + y) * W + x] = v;
+}
+
 // ---- multi-scale merge + prediction (utils/inference_tools.py:134-161, :85-88) ----
 // torch's align_corners=False source index: src = max(0, (in/out)*(dst + 0.5) - 0.5)
 __device__ __forceinline__ Lerp make_lerp_half_pixel(int dst, int in_size, int out_size) {
@@ -230,6 +262,25 @@ int launch_pseudo_labels(const float* m, const float* labels, const unsigned* cl
 }  // namespace pamr
 
 namespace pamr {
+int launch_denorm_resize(const float* src, float* dst, const float* mean_host, const float* std_host, int B, int K, int h,
+                         int w, int H, int W, cudaStream_t s) {
+    if (K < 1 || K > 8) return set_error(PAMR_ERR_INVALID_ARGUMENT, "denorm: 1..8 channels supported, got %d", K);
+    ChannelAffine aff;
+    for (int k = 0; k < 8; ++k) {
+        aff.scale[k] = k < K ? std_host[k] : 1.f;
+        aff.shift[k] = k < K ? mean_host[k] : 0.f;
+    }
+    dim3 grid((W + EP_BX - 1) / EP_BX, (H + EP_BY - 1) / EP_BY, B * K), block(EP_BX, EP_BY);
+    if (grid.y > 65535 || grid.z > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "denorm: H/8 and B*K must be <= 65535");
+    if (h != H || w != W)
+        denorm_resize_kernel<true><<<grid, block, 0, s>>>(src, dst, aff, K, h, w, H, W, scale_of(h, H), scale_of(w, W));
+    else
+        denorm_resize_kernel<false><<<grid, block, 0, s>>>(src, dst, aff, K, h, w, H, W, 0.f, 0.f);
+    count_launch();
+    PAMR_CUDA_TRY(cudaGetLastError());
+    return PAMR_OK;
+}
+
 int launch_merge_multiscale(const float* masks, const int* pads_host, const float* labels, float* merged, uint8_t* pred,
                             int S, int C, int Hp, int Wp, int H, int W, int flip, float bg_pow, float thresh,
                             cudaStream_t s) {

@@ -16,9 +16,32 @@ from .pamr import PAMR, _check_cuda_f32, _dev, _stream, resize_bilinear
 IGNORE_INDEX = 255
 
 
-def run_pamr(pamr, im, mask):
-    """run_pamr(self, im, mask) with self._aff == pamr (SoftMaxAE.py:176-179)."""
-    im = resize_bilinear(im, mask.shape[-2:]) if tuple(im.shape[-2:]) != tuple(mask.shape[-2:]) else im
+VOC_MEAN, VOC_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)  # datasets/pascal_voc.py:69-70
+
+
+def denorm_resize(image_norm, mean=VOC_MEAN, std=VOC_STD, size=None):
+    """`denorm(image.clone())` (datasets/pascal_voc.py:85-101, train.py:120) and the bilinear resize of
+    run_pamr (SoftMaxAE.py:177) in one pass: returns a new tensor [B,K,H,W]; the input is not modified."""
+    import ctypes
+    x = _check_cuda_f32("image", image_norm)
+    B, K, h, w = x.shape
+    H, W = _size_of(size) if size is not None else (h, w)
+    if len(mean) != K or len(std) != K:
+        raise RuntimeError("mean / std must have one entry per image channel (%d)" % K)
+    out = torch.empty((B, K, H, W), dtype=torch.float32, device=x.device)
+    c_mean, c_std = (ctypes.c_float * K)(*[float(v) for v in mean]), (ctypes.c_float * K)(*[float(v) for v in std])
+    _lib.check(_lib.lib().pamr_denorm_resize_f32(x.data_ptr(), ctypes.cast(c_mean, ctypes.c_void_p), ctypes.cast(c_std, ctypes.c_void_p),
+                                                 out.data_ptr(), B, K, h, w, H, W, _dev(x), _stream(x.device)))
+    return out
+
+
+def run_pamr(pamr, im, mask, denorm=None):
+    """run_pamr(self, im, mask) with self._aff == pamr (SoftMaxAE.py:176-179).  With denorm=(mean, std) `im`
+    is the NORMALISED network input and train.py:120's denorm is folded into the resize."""
+    if denorm is not None:
+        im = denorm_resize(im, denorm[0], denorm[1], mask.shape[-2:])
+    elif tuple(im.shape[-2:]) != tuple(mask.shape[-2:]):
+        im = resize_bilinear(im, mask.shape[-2:])
     return pamr(im, mask)
 
 
@@ -104,7 +127,7 @@ def labels_from_pseudo_gt(pseudo_gt, ignore_index=IGNORE_INDEX):
     return mask_gt
 
 
-def refine_and_label(pamr, image_raw, masks, labels, out_size=None, return_masks=False, return_counts=False):
+def refine_and_label(pamr, image_raw, masks, labels, out_size=None, return_masks=False, return_counts=False, denorm=None):
     """Sequence A of stage_net (SoftMaxAE.py:250-259) in as few passes as possible:
     run_pamr(image_raw, masks) -> _rescale_and_clean(., labels) -> pseudo_gtmask -> label map.
 
@@ -115,7 +138,10 @@ def refine_and_label(pamr, image_raw, masks, labels, out_size=None, return_masks
         raise TypeError("pamr must be a wseg_b200.PAMR module")
     H, W = _size_of(out_size) if out_size is not None else _size_of(image_raw)
     h, w = int(masks.shape[-2]), int(masks.shape[-1])
-    im = resize_bilinear(image_raw, (h, w)) if tuple(image_raw.shape[-2:]) != (h, w) else image_raw
+    if denorm is not None:  # image_raw is the normalised input: fold train.py:120's denorm into the resize
+        im = denorm_resize(image_raw, denorm[0], denorm[1], (h, w))
+    else:
+        im = resize_bilinear(image_raw, (h, w)) if tuple(image_raw.shape[-2:]) != (h, w) else image_raw
     if (h, w) == (H, W):
         dec, cmax = pamr(im, masks, return_class_max=True)  # class max fused into the last iteration
         res = pseudo_labels(dec, labels, None, cmax, return_counts=return_counts)

@@ -160,6 +160,16 @@ int pamr_mask_ce_backward_f32(const float* logits, const uint8_t* label, const f
                               int dev, pamr_stream_t stream);
 
 /*
+ * SURVEY 8(f) row 4 -- the data set's denorm (datasets/pascal_voc.py:85-101; train.py:120
+ * `image_raw = self.denorm(image.clone())`) folded into the image resize of run_pamr (SoftMaxAE.py:177):
+ *   dst[b,k] = bilinear(img_norm[b,k] * std[k] + mean[k]  ->  [H,W]),  align_corners=True
+ * (multiply and add rounded separately, as mul_().add_() does; with h == H and w == W it is the plain denorm).
+ * mean_host / std_host: HOST arrays of K floats, K <= 8.  img_norm [B,K,h,w] -> dst [B,K,H,W].
+ */
+int pamr_denorm_resize_f32(const float* img_norm, const float* mean_host, const float* std_host, float* dst, int B,
+                           int K, int h, int w, int H, int W, int dev, pamr_stream_t stream);
+
+/*
  * SURVEY 8(f) row 3 -- inference post-processing, one image:
  *   MergeMultiScale._merge_masks (utils/inference_tools.py:134-161): every scale s of masks [S,C,Hp,Wp] is
  *   un-padded (pads[s] = pad_t, pad_l, h_s, w_s; HOST array of 4*S ints), resized to [H,W] (bilinear,

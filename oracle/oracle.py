@@ -210,3 +210,12 @@ def merge_multiscale(masks, pads, labels, imsize_hw, flip, bg_pow, prospect_thre
                                        merged.ctypes.data_as(ctypes.c_void_p), pred.ctypes.data_as(ctypes.c_void_p), S, C, Hp, Wp,
                                        H, W, int(bool(flip)), float(bg_pow), float(prospect_thresh))
     return merged, pred
+
+
+def denorm_resize(image_norm, mean, std, size=None):
+    """denorm (datasets/pascal_voc.py:85-101: t.mul_(s).add_(m) per channel, two float roundings) followed by
+    the align_corners=True bilinear resize of run_pamr (SoftMaxAE.py:177)."""
+    x = _c(image_norm).copy()
+    for k, (m, s_) in enumerate(zip(mean, std)):
+        x[:, k] = x[:, k] * np.float32(s_) + np.float32(m)
+    return x if size is None or tuple(size) == x.shape[-2:] else resize_bilinear(x, size)

@@ -392,3 +392,24 @@ def test_repeatability_under_allocator_churn():
         junk = torch.rand((B, C, H, W), device=DEV)  # noqa: F841  (L2 / allocator churn)
         bad += int(not torch.equal(pamr(image, mask), ref))
     assert bad == 0
+
+
+def test_cuda_graph_capture_and_replay():
+    """The whole refine_and_label sequence (side-stream fork/join, TMA descriptors passed by value) can be
+    captured into a CUDA graph and replayed on new inputs."""
+    B, C, H, W = 4, 21, 81, 97
+    pamr = wseg_b200.PAMR(10, D6).to(DEV)
+    s_img = G(synth.image_structured(B, 3, H, W, 61))
+    s_msk = G(synth.mask_softmax(B, C, H, W, 62))
+    s_lab = G(synth.labels_bernoulli(B, C, 63, p=0.3))
+    wseg_b200.refine_and_label(pamr, s_img, s_msk, s_lab)  # warm-up outside the capture (attributes, side stream)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        s_out = wseg_b200.refine_and_label(pamr, s_img, s_msk, s_lab)
+    for seed in (71, 72):
+        img, msk = G(synth.image_structured(B, 3, H, W, seed)), G(synth.mask_softmax(B, C, H, W, seed + 10))
+        s_img.copy_(img); s_msk.copy_(msk)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(s_out, wseg_b200.refine_and_label(pamr, img, msk, s_lab))

@@ -88,6 +88,18 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-GPU runs: pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity), so that
+    the pinned staging buffers of the end-to-end path are first-touched on that NUMA node and the N concurrent
+    host->device streams do not cross sockets.  Best effort: silently skipped if NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception:
+        pass
+
+
 def cpu_baseline_sample(steps, warmup):
     """Times the CPU port of the reference path (oracle/pamr_oracle.c, OpenMP over all host cores) on a
     bounded sample of the workload: one 321x321 image of the batch per step."""
@@ -178,6 +190,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        bind_to_gpu_numa_node(local_rank)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank if world > 1 else 0)

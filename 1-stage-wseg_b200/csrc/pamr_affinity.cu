@@ -156,7 +156,7 @@ constexpr int SA_MAXK = 8;
 __host__ __device__ constexpr int sa_dil(int id) { return id == 0 ? 1 : id == 1 ? 2 : id == 2 ? 4 : id == 3 ? 8 : id == 4 ? 12 : 24; }
 
 template <bool TILED>
-__global__ void __launch_bounds__(SA_BX * SA_BY, 3)
+__global__ void __launch_bounds__(SA_BX * SA_BY, 2)  // 128 registers: 3 CTAs/SM (85) spilled the 48 accumulators, 6 % slower
 affinity_smem_kernel(const float* __restrict__ img, float* __restrict__ aff, int K, int H, int W, AffTiling tiling) {
     extern __shared__ float sa_tile[];  // [K][SA_H][SA_W]
     const int x0 = blockIdx.x * SA_BX, y0 = blockIdx.y * SA_BY, b = blockIdx.z;

@@ -147,8 +147,8 @@ affinity_kernel(const float* __restrict__ img, float* __restrict__ aff, int K, i
 // A CTA owns a 32 x 8 pixel tile; the K image planes of the tile plus its 24-pixel halo are staged
 // in shared memory once, with replicate padding applied while staging (clamped source
 // coordinates), so every neighbour is a shared-memory load at an immediate offset: no 64-bit
-// address arithmetic, no clamps and ~half the registers of the generic kernel (2 CTAs = 16 warps
-// per SM instead of 8).
+// address arithmetic and no clamps in the inner loops (128 registers, 2 CTAs = 16 warps
+// per SM).
 constexpr int SA_BX = 32, SA_BY = 8, SA_HALO = 24;
 constexpr int SA_W = SA_BX + 2 * SA_HALO;  // 80
 constexpr int SA_H = SA_BY + 2 * SA_HALO;  // 56

@@ -66,6 +66,7 @@ constexpr int PL_THREADS = 256;
 
 // One thread per output pixel, loops over the C classes (coalesced plane reads).
 // grid: (ceil(H*W/256), B)
+constexpr int PL_BATCH = 7;  // 21 classes = 3 batches
 template <bool kResize>
 __global__ void __launch_bounds__(PL_THREADS)
 pseudo_labels_kernel(const float* __restrict__ m, const float* __restrict__ labels,
@@ -96,13 +97,26 @@ pseudo_labels_kernel(const float* __restrict__ m, const float* __restrict__ labe
         const int y = (int)(i / W), x = (int)(i % W);
         Lerp ly, lx;
         if (kResize) { ly = make_lerp(y, sh, h); lx = make_lerp(x, sw, w); }
-        for (int c = 0; c < C; ++c) {
-            const size_t plane = (size_t)b * C + c;
-            float v = kResize ? bilerp(m + plane * h * w, w, ly, lx) : __ldg(m + plane * HW + i);
-            if (labels != nullptr && c > 0) v = __fmul_rn(v, gate[c]);
-            if (v > thr[c]) {
-                if (first < 0) first = c;
-                ++n;
+        // classes in batches of PL_BATCH: all loads of a batch are issued before the first compare
+        // (one thread otherwise has a single 4-byte load in flight: latency-, not bandwidth-bound)
+        for (int c0 = 0; c0 < C; c0 += PL_BATCH) {
+            float v[PL_BATCH];
+#pragma unroll
+            for (int j = 0; j < PL_BATCH; ++j) {
+                const int c = min(c0 + j, C - 1);
+                const size_t plane = (size_t)b * C + c;
+                v[j] = kResize ? bilerp(m + plane * h * w, w, ly, lx) : __ldg(m + plane * HW + i);
+            }
+#pragma unroll
+            for (int j = 0; j < PL_BATCH; ++j) {
+                const int c = c0 + j;
+                if (c < C) {
+                    const float g = (labels != nullptr && c > 0) ? __fmul_rn(v[j], gate[c]) : v[j];
+                    if (g > thr[c]) {
+                        if (first < 0) first = c;
+                        ++n;
+                    }
+                }
             }
         }
         const bool one = (n == 1);

@@ -19,6 +19,7 @@ namespace pamr {
 namespace {
 
 constexpr int LS_BX = 32, LS_BY = 8;
+constexpr int CE_BATCH = 7;  // class planes loaded per batch in the forward kernel (21 = 3 x 7)
 
 struct CeWorkspace {
     double* acc;   // [B]    sum_px cw*ce
@@ -49,10 +50,18 @@ labels_from_onehot_kernel(const float* __restrict__ pg, uint8_t* __restrict__ la
     if (valid) {
         float best = 0.f, sum = 0.f;
         int arg = 0;
-        for (int c = 0; c < C; ++c) {
-            const float v = __ldg(pg + ((size_t)b * C + c) * HW + i);
-            sum = __fadd_rn(sum, v);
-            if (c == 0 || v > best) { best = v; arg = c; }
+        for (int c0 = 0; c0 < C; c0 += CE_BATCH) {
+            float vb[CE_BATCH];
+#pragma unroll
+            for (int j = 0; j < CE_BATCH; ++j) vb[j] = __ldg(pg + ((size_t)b * C + min(c0 + j, C - 1)) * HW + i);
+#pragma unroll
+            for (int j = 0; j < CE_BATCH; ++j) {
+                const int c = c0 + j;
+                if (c < C) {
+                    sum = __fadd_rn(sum, vb[j]);
+                    if (c == 0 || vb[j] > best) { best = vb[j]; arg = c; }
+                }
+            }
         }
         lab = (sum < 1.f) ? 255 : arg;
         label[(size_t)b * HW + i] = (uint8_t)lab;
@@ -106,14 +115,25 @@ ce_forward_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ 
             const Lerp ly = make_lerp(y, sh, h), lx = make_lerp(x, sw, w);
             const float* __restrict__ base = logits + (size_t)b * C * hw;
             float m = -INFINITY, s = 0.f, zl = 0.f;  // online log-sum-exp
-            for (int c = 0; c < C; ++c) {
-                const float v = logit_at<kResize>(base + (size_t)c * hw, w, i, ly, lx);
-                if (c == lab) zl = v;
-                if (v > m) {
-                    s = s * expf(m - v) + 1.f;
-                    m = v;
-                } else {
-                    s += expf(v - m);
+            // classes in batches of CE_BATCH: the loads of a batch are issued before the dependent exp chain
+            for (int c0 = 0; c0 < C; c0 += CE_BATCH) {
+                float vb[CE_BATCH];
+#pragma unroll
+                for (int j = 0; j < CE_BATCH; ++j)
+                    vb[j] = logit_at<kResize>(base + (size_t)min(c0 + j, C - 1) * hw, w, i, ly, lx);
+#pragma unroll
+                for (int j = 0; j < CE_BATCH; ++j) {
+                    const int c = c0 + j;
+                    if (c < C) {
+                        const float v = vb[j];
+                        if (c == lab) zl = v;
+                        if (v > m) {
+                            s = s * expf(m - v) + 1.f;
+                            m = v;
+                        } else {
+                            s += expf(v - m);
+                        }
+                    }
                 }
             }
             lse = m + logf(s);

@@ -674,9 +674,10 @@ __global__ void __launch_bounds__(128) strip_rows_kernel(const Params prm) {
 constexpr int SC_ROWS = 32;                      // pixel rows per CTA
 constexpr int SC_WIN_H = SC_ROWS + 2 * HALO;     // 80
 constexpr int SC_WIN_W = 32;                     // staged columns [W-32, W)  (needs W >= 32)
+constexpr int SC_LOADS = 20;                     // row loads in flight per thread while staging (SC_WIN_H % SC_LOADS == 0)
 constexpr int SC_CG = 8;                         // class planes staged at a time (one warp each)
 template <int R>
-__global__ void __launch_bounds__(SC_CG * 32, 6) strip_cols_kernel(const Params prm) {  // (.,6): <= 40 registers
+__global__ void __launch_bounds__(SC_CG * 32, 5) strip_cols_kernel(const Params prm) {  // (.,5): <= 48 registers, so that a CTA fits next to a resident tile CTA
     extern __shared__ float sc_smem[];  // [SC_CG][SC_WIN_H][SC_WIN_W + 1] then weights [wc][48][32]
     const int C = prm.C, H = prm.H, W = prm.W, wc = W - prm.Wt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -696,16 +697,17 @@ __global__ void __launch_bounds__(SC_CG * 32, 6) strip_cols_kernel(const Params 
         const int c = c0 + warp;
         if (c < C) {  // stage this warp's class plane window (rows clamped: replicate padding)
             const float* __restrict__ pl = prm.src + ((size_t)b * C + c) * H * prm.src_pitch;
-            // 8 row loads in flight at a time: the kernel overlaps the tile kernel on a second stream and is
-            // kept small in registers so that its CTAs can be placed as soon as an SM has room
+            // SC_LOADS row loads in flight at a time: the kernel overlaps the tile kernel on a second stream and is
+            // kept at <= 48 registers so that its CTAs can be placed next to a resident tile CTA (12 K registers
+            // are free there).  321x321 B=16 forward: 8 loads 2.83 ms, 16: 2.82, 20: 2.77, 40 (64 registers): 2.80
 #pragma unroll 1
-            for (int r0 = 0; r0 < SC_WIN_H; r0 += 8) {
-                float v[8];
+            for (int r0 = 0; r0 < SC_WIN_H; r0 += SC_LOADS) {
+                float v[SC_LOADS];
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
+                for (int q = 0; q < SC_LOADS; ++q)
                     v[q] = __ldg(pl + (size_t)clampi(yb - HALO + r0 + q, 0, H - 1) * prm.src_pitch + xs0 + lane);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) mywin[(r0 + q) * PITCH + lane] = v[q];
+                for (int q = 0; q < SC_LOADS; ++q) mywin[(r0 + q) * PITCH + lane] = v[q];
             }
         }
         __syncthreads();  // also covers the weights on the first round

@@ -413,3 +413,12 @@ def test_cuda_graph_capture_and_replay():
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(s_out, wseg_b200.refine_and_label(pamr, img, msk, s_lab))
+
+
+def test_plain_c_caller_runs(tmp_path):
+    """examples/c_abi_demo.c: a C99 program that only knows include/pamr_b200.h, host buffers in, labels out."""
+    import subprocess
+    from test_host import _build_c_demo
+    r = subprocess.run([_build_c_demo(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "kernels launched" in r.stdout and "label" in r.stdout

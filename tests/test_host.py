@@ -164,3 +164,24 @@ def test_gather_labels_gloo_world2(batch):
         p.join(60)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _build_c_demo(tmp_path):
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "1-stage-wseg_b200")
+    exe = os.path.join(str(tmp_path), "c_abi_demo")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "examples", "c_abi_demo.c"), "-L" + pkg, "-lpamr_b200", "-Wl,-rpath," + pkg,
+                        "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/pamr_b200.h compiles as pedantic C99 and a C program links against the library with no C++ /
+    torch / Python involved (examples/c_abi_demo.c); running it needs a GPU (tests/test_gpu_parity.py)."""
+    _lib.build()
+    assert os.path.exists(_build_c_demo(tmp_path))

@@ -422,3 +422,19 @@ def test_plain_c_caller_runs(tmp_path):
     r = subprocess.run([_build_c_demo(tmp_path)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "kernels launched" in r.stdout and "label" in r.stdout
+
+
+def test_random_shapes_vs_oracle():
+    """Shape fuzz (tail / side lane / strip / padded-tile / generic paths are chosen per shape by tuned_tiling)."""
+    rng = np.random.RandomState(123)
+    for _ in range(40):
+        B, C = int(rng.randint(1, 7)), int(rng.randint(1, 25))
+        H, W = int(rng.randint(8, 200)), int(rng.randint(8, 200))
+        if rng.rand() < 0.3:
+            H, W = 40 * int(rng.randint(1, 5)) + int(rng.randint(0, 9)), 32 * int(rng.randint(1, 6)) + int(rng.randint(0, 9))
+        it = int(rng.choice([1, 2, 5]))
+        image = rng.rand(B, 3, H, W).astype(np.float32)
+        e = np.exp(rng.randn(B, C, H, W)).astype(np.float32)
+        mask = e / e.sum(1, keepdims=True)
+        out = N(wseg_b200.PAMR(it, D6).to(DEV)(G(image), G(mask)))
+        assert np.abs(out - oracle.pamr_forward(image, mask, it, D6)).max() <= TOL, (B, C, H, W, it)

@@ -9,7 +9,8 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpamr_b200.so")
+# PAMR_B200_LIB selects another build of the same ABI (experiment variants, tools/build_variant.sh)
+LIB_PATH = os.environ.get("PAMR_B200_LIB") or os.path.join(_HERE, "libpamr_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 ABI_VERSION = 1
 

@@ -50,10 +50,10 @@ affinity_kernel(const float* __restrict__ img, float* __restrict__ aff, int K, i
         if (TILED) {
             // inside a partial tile but outside the image: the propagation kernel expects zeros
             if (x < tiling.tiles_x * 32 && y < tiling.tiles_y * 4 * tiling.R) {
-                float* __restrict__ out = aff + aff_tiled_index(tiling, b, 0, y, x);
-                const size_t sstride = (size_t)tiling.R * 32;
+                int ti = 0;
+                float* __restrict__ out = aff + aff_tiled_pixel_base(tiling, b, y, x, &ti);
 #pragma unroll
-                for (int s = 0; s < 48; ++s) out[s * sstride] = 0.f;
+                for (int s = 0; s < 48; ++s) out[aff_tiled_col_offset(s * tiling.R + ti)] = 0.f;
             }
         }
         return;
@@ -130,10 +130,10 @@ affinity_kernel(const float* __restrict__ img, float* __restrict__ aff, int K, i
     }
     const float rs = __frcp_rn(s);  // s in [1, P]
     if (TILED) {
-        float* __restrict__ out = aff + aff_tiled_index(tiling, b, 0, y, x);
-        const size_t sstride = (size_t)tiling.R * 32;
+        int ti = 0;
+        float* __restrict__ out = aff + aff_tiled_pixel_base(tiling, b, y, x, &ti);
 #pragma unroll
-        for (int p = 0; p < 8 * MAXND; ++p) out[tap_seq(p) * sstride] = div_markstein(abar[p], s, rs);
+        for (int p = 0; p < 8 * MAXND; ++p) out[aff_tiled_col_offset(tap_seq(p) * tiling.R + ti)] = div_markstein(abar[p], s, rs);
     } else {
         float* __restrict__ out = aff + (size_t)b * P * HW + (size_t)y * W + x;
 #pragma unroll
@@ -188,10 +188,10 @@ affinity_smem_kernel(const float* __restrict__ img, float* __restrict__ aff, int
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= W || y >= H) {
         if (TILED && x < tiling.tiles_x * 32 && y < tiling.tiles_y * 4 * tiling.R) {
-            float* __restrict__ out = aff + aff_tiled_index(tiling, b, 0, y, x);
-            const size_t sstride = (size_t)tiling.R * 32;
+            int ti = 0;
+            float* __restrict__ out = aff + aff_tiled_pixel_base(tiling, b, y, x, &ti);
 #pragma unroll
-            for (int s = 0; s < 48; ++s) out[s * sstride] = 0.f;
+            for (int s = 0; s < 48; ++s) out[aff_tiled_col_offset(s * tiling.R + ti)] = 0.f;
         }
         return;
     }
@@ -261,10 +261,10 @@ affinity_smem_kernel(const float* __restrict__ img, float* __restrict__ aff, int
     }
     const float rs = __frcp_rn(s);
     if (TILED) {
-        float* __restrict__ out = aff + aff_tiled_index(tiling, b, 0, y, x);
-        const size_t sstride = (size_t)tiling.R * 32;
+        int ti = 0;
+        float* __restrict__ out = aff + aff_tiled_pixel_base(tiling, b, y, x, &ti);
 #pragma unroll
-        for (int p = 0; p < 48; ++p) out[tap_seq(p) * sstride] = div_markstein(abar[p], s, rs);
+        for (int p = 0; p < 48; ++p) out[aff_tiled_col_offset(tap_seq(p) * tiling.R + ti)] = div_markstein(abar[p], s, rs);
     } else {
         float* __restrict__ out = aff + (size_t)b * 48 * HW + (size_t)y * W + x;
 #pragma unroll
@@ -289,10 +289,10 @@ aff_relayout_kernel(const float* __restrict__ src, float* __restrict__ dst, int 
     const bool in = (x < W) && (y < H);
     const size_t HW = (size_t)H * W;
     const float* __restrict__ ip = src + (size_t)b * 48 * HW + (size_t)y * W + x;
-    float* __restrict__ out = dst + aff_tiled_index(tiling, b, 0, y, x);
-    const size_t sstride = (size_t)tiling.R * 32;
+    int ti = 0;
+    float* __restrict__ out = dst + aff_tiled_pixel_base(tiling, b, y, x, &ti);
 #pragma unroll 8
-    for (int p = 0; p < 48; ++p) out[tap_seq(p) * sstride] = in ? __ldg(ip + (size_t)p * HW) : 0.f;
+    for (int p = 0; p < 48; ++p) out[aff_tiled_col_offset(tap_seq(p) * tiling.R + ti)] = in ? __ldg(ip + (size_t)p * HW) : 0.f;
 }
 
 }  // namespace

@@ -49,7 +49,8 @@ int check_device_arch(int dev) {
     int major = 0, minor = 0;
     PAMR_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     PAMR_CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
-    if (major != 10)
+    // the library carries sm_100a SASS only, and arch-specific ("a") code does not run on other 10.x parts
+    if (major != 10 || minor != 0)
         return set_error(PAMR_ERR_UNSUPPORTED_DEVICE,
                          "device %d is sm_%d%d; libpamr_b200 is built for sm_100a (B200) only and has no fallback",
                          dev, major, minor);
@@ -199,6 +200,7 @@ int pamr_forward_f32(const float* img, const float* mask, float* out, void* work
     PAMR_REQUIRE(img && mask && out, "forward: NULL pointer");
     PAMR_REQUIRE(iters >= 0, "forward: iters=%d is negative", iters);
     PAMR_REQUIRE(K >= 1 && h >= 1 && w >= 1, "forward: non-positive dimension");
+    PAMR_REQUIRE(out != mask && out != img, "forward: out must not alias mask or img");
     PAMR_TRY(check_dims(B, C, H, W));
     Dilations dil;
     PAMR_TRY(make_dilations(dilations, nd, &dil));

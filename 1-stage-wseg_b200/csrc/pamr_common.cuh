@@ -24,11 +24,13 @@ __device__ __forceinline__ int tap_dx(int j) {
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 // ---- tile-major affinity layout consumed by the tuned sm_100a propagation kernel ----
-// Only for the standard 6 dilations (48 taps).  The tuned kernel's thread (lane quarter wq, lane)
-// of tile (ty,tx) owns R pixels (rows ty*4R + wq*R + i, column tx*32 + lane) and parks its 48*R
-// weights in TMEM in the "sequence" order s below, so the affinity kernel writes them as
-//   [b][ty][tx][wq][s][i][lane]           (each [s][i] row = 32 lanes = one 128-byte line)
-// which makes the TMEM fill a stream of coalesced loads at immediate offsets from one pointer.
+// Only for the standard 6 dilations (48 taps).  The tuned kernel's thread (lane quarter wq, lane) of tile
+// (ty,tx) owns R pixels (rows ty*4R + wq*R + i, column tx*32 + lane) and keeps their 48*R weights in its
+// Tensor Memory lane l = wq*32 + lane, at column s*R + i ("sequence" order s below).  The weights travel
+// global -> shared memory (cp.async.bulk) -> TMEM (tcgen05.cp) without passing through registers, so the
+// global layout IS the shared-memory image tcgen05.cp reads: 16-byte pieces of 4 consecutive columns per lane,
+//   [b][ty][tx][column / 4][l = 0..127][column % 4]
+// (128 lanes x 16 bytes = 2 KB per piece; 8 pieces = one 16 KB fill unit of 32 columns).
 // Pixels of partial tiles that lie outside the image hold zeros.
 //
 // Tap sequence s (0..47) <-> reference tap p = 8*id + j (pamr.py:25-34):
@@ -53,11 +55,23 @@ struct AffTiling {
     int Wt, Ht;               // host-side: extent covered by tiles (the rest goes to the strip kernels)
 };
 __host__ __device__ __forceinline__ size_t aff_tiled_floats(int B, const AffTiling& t) {
-    return (size_t)B * t.tiles_y * t.tiles_x * 4 * 48 * t.R * 32;
+    return (size_t)B * t.tiles_y * t.tiles_x * 48 * t.R * 128;
 }
+// offset of weight (s, i) relative to the pixel's base (aff_tiled_index with s = 0 at a pixel with i = 0 ... see below)
+__host__ __device__ __forceinline__ size_t aff_tiled_col_offset(int col) { return ((size_t)(col >> 2) << 9) + (size_t)(col & 3); }
+// index of weight s of pixel (y, x)
 __host__ __device__ __forceinline__ size_t aff_tiled_index(const AffTiling& t, int b, int s, int y, int x) {
     const int ty = y / (4 * t.R), ry = y % (4 * t.R), wq = ry / t.R, i = ry % t.R;
-    return ((((((size_t)b * t.tiles_y + ty) * t.tiles_x + (x >> 5)) * 4 + wq) * 48 + s) * t.R + i) * 32 + (x & 31);
+    const size_t tile = ((size_t)b * t.tiles_y + ty) * t.tiles_x + (x >> 5);
+    return tile * ((size_t)48 * t.R * 128) + (size_t)(wq * 32 + (x & 31)) * 4 + aff_tiled_col_offset(s * t.R + i);
+}
+// base pointer offset of a pixel (lane part only) and its row i within the owning thread's strip: weight s is at
+// base + aff_tiled_col_offset(s*R + i)
+__host__ __device__ __forceinline__ size_t aff_tiled_pixel_base(const AffTiling& t, int b, int y, int x, int* i_out) {
+    const int ty = y / (4 * t.R), ry = y % (4 * t.R), wq = ry / t.R;
+    *i_out = ry % t.R;
+    const size_t tile = ((size_t)b * t.tiles_y + ty) * t.tiles_x + (x >> 5);
+    return tile * ((size_t)48 * t.R * 128) + (size_t)(wq * 32 + (x & 31)) * 4;
 }
 
 // Monotone float <-> unsigned map so that atomicMax(unsigned) implements a float max for any sign.

@@ -15,9 +15,10 @@
 namespace pamr {
 
 // pamr_propagate_sm100.cu
-int launch_repack(const float* src, float* dst, int planes, int H, int W, int Wp, cudaStream_t s);
-int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, int src_pitch, float* dst,
-                           int dst_pitch, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s,
+int pair_pitch(int W);
+int launch_repack_pairs(const float* src, float* dst, int planes, int H, int W, cudaStream_t s);
+int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, float* dst, int dst_pitch,
+                           bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s,
                            SideLane* lane);
 
 namespace {
@@ -108,57 +109,78 @@ struct ScratchPlan {
 ScratchPlan plan_scratch(int B, int C, int H, int W, const Dilations& dil, int iters, bool aff_is_tiled) {
     ScratchPlan p{0, 0, 0};
     if (iters <= 0) return p;
-    // two ping-pong buffers with rows pitched to a multiple of 4 floats (TMA needs 16-byte global
-    // strides; W = 321 is not)
-    const size_t Wp = align_up((size_t)W, 4);
-    p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * H * Wp, 256);
     const AffTiling t = tuned_tiling(B, H, W, dil);
-    if (t.R > 0 && !aff_is_tiled) p.aff_tiled = align_up(sizeof(float) * aff_tiled_floats(B, t), 256);
+    if (t.R > 0) {
+        // tuned kernel: two ping-pong buffers in the row-pair layout [B*C][ceil(H/2)][Wp][2], Wp even (TMA reads
+        // 64-bit elements and needs 16-byte global strides)
+        p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * ((H + 1) / 2) * pair_pitch(W) * 2, 256);
+        if (!aff_is_tiled) p.aff_tiled = align_up(sizeof(float) * aff_tiled_floats(B, t), 256);
+    } else {
+        p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * H * W, 256);
+    }
     p.total = 2 * p.pingpong_each + p.aff_tiled;
     return p;
 }
 
-}  // namespace
-
-// Fork/join helper: a per-thread, per-device side stream on which small independent kernels
-// (row repack, remainder strip) run concurrently with the big kernel on the caller's stream.
-// The persistent propagation kernel occupies every SM with one CTA but leaves threads and
-// registers for these, so their time disappears from the critical path.
-struct ForkJoin {
-    cudaStream_t main_s = nullptr, side = nullptr;
+// Per-thread, per-device side stream and events (created once, reused by every call of that thread): small
+// independent kernels (row-pair repack, remainder column strip) run on the side stream concurrently with the
+// big kernel on the caller's stream.  The persistent propagation kernel occupies every SM with one CTA but
+// leaves threads and registers for these, so their time disappears from the critical path.
+struct SideResources {
+    cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_tiles = nullptr, ev_strip = nullptr;
-    int init(int dev, cudaStream_t m) {
-        static thread_local cudaStream_t cache[64] = {nullptr};
-        main_s = m;
-        if (dev >= 0 && dev < 64 && cache[dev] != nullptr) {
-            side = cache[dev];
-        } else {
-            PAMR_CUDA_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-            if (dev >= 0 && dev < 64) cache[dev] = side;
+};
+int side_resources(int dev, SideResources** out) {
+    static thread_local SideResources cache[64];
+    static thread_local SideResources overflow;
+    SideResources* r = (dev >= 0 && dev < 64) ? &cache[dev] : &overflow;
+    if (r->side == nullptr || r == &overflow) {
+        if (r == &overflow && r->side != nullptr) {  // device ordinals >= 64 share one slot: rebuild per call
+            cudaStreamDestroy(r->side);
+            cudaEventDestroy(r->ev_fork); cudaEventDestroy(r->ev_join);
+            cudaEventDestroy(r->ev_tiles); cudaEventDestroy(r->ev_strip);
+            *r = SideResources();
         }
-        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&ev_tiles, cudaEventDisableTiming));
-        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&ev_strip, cudaEventDisableTiming));
+        PAMR_CUDA_TRY(cudaStreamCreateWithFlags(&r->side, cudaStreamNonBlocking));
+        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&r->ev_fork, cudaEventDisableTiming));
+        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&r->ev_join, cudaEventDisableTiming));
+        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&r->ev_tiles, cudaEventDisableTiming));
+        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&r->ev_strip, cudaEventDisableTiming));
+    }
+    *out = r;
+    return PAMR_OK;
+}
+
+// Fork/join of the side stream around one API call.  Once forked, the destructor joins: on every return
+// path (errors included) the caller's stream waits for whatever was enqueued on the side stream, so that the
+// workspace is never handed back to the allocator while side-stream work still touches it.
+struct ForkJoin {
+    cudaStream_t main_s = nullptr;
+    SideResources* r = nullptr;
+    bool forked = false;
+    int init(int dev, cudaStream_t m) {
+        main_s = m;
+        return side_resources(dev, &r);
+    }
+    int fork() {  // work enqueued on the side stream after this sees everything enqueued on main so far
+        PAMR_CUDA_TRY(cudaEventRecord(r->ev_fork, main_s));
+        PAMR_CUDA_TRY(cudaStreamWaitEvent(r->side, r->ev_fork, 0));
+        forked = true;
         return PAMR_OK;
     }
-    int fork() {  // work enqueued on `side` after this sees everything enqueued on main so far
-        PAMR_CUDA_TRY(cudaEventRecord(ev_fork, main_s));
-        PAMR_CUDA_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
-        return PAMR_OK;
-    }
-    int join() {  // work enqueued on main after this sees everything enqueued on `side` so far
-        PAMR_CUDA_TRY(cudaEventRecord(ev_join, side));
-        PAMR_CUDA_TRY(cudaStreamWaitEvent(main_s, ev_join, 0));
+    int join() {  // work enqueued on main after this sees everything enqueued on the side stream so far
+        forked = false;
+        PAMR_CUDA_TRY(cudaEventRecord(r->ev_join, r->side));
+        PAMR_CUDA_TRY(cudaStreamWaitEvent(main_s, r->ev_join, 0));
         return PAMR_OK;
     }
     ~ForkJoin() {
-        if (ev_fork) cudaEventDestroy(ev_fork);
-        if (ev_join) cudaEventDestroy(ev_join);
-        if (ev_tiles) cudaEventDestroy(ev_tiles);
-        if (ev_strip) cudaEventDestroy(ev_strip);
+        if (forked && r != nullptr && cudaEventRecord(r->ev_join, r->side) == cudaSuccess)
+            cudaStreamWaitEvent(main_s, r->ev_join, 0);
     }
 };
+
+}  // namespace
 
 size_t propagate_scratch_bytes(int B, int C, int H, int W, const Dilations& dil, int iters, bool aff_is_tiled) {
     return plan_scratch(B, C, H, W, dil, iters, aff_is_tiled).total;
@@ -201,67 +223,69 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
                          plan.total);
     if (((uintptr_t)scratch & 255) != 0)
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: scratch must be 256-byte aligned");
-    const int Wp = (int)align_up((size_t)W, 4);
     float* P[2] = {(float*)scratch, (float*)((char*)scratch + plan.pingpong_each)};
     if (!tuned && aff_is_tiled)
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "propagate: tiled affinity without the tuned kernel");
-    const bool need_repack = tuned && ((W & 3) != 0 || ((uintptr_t)m_in & 15) != 0);
 
-    // the column strip runs on the side stream, concurrently with the tiles (PAMR_B200_NO_LANE=1: serialised)
-    static const bool no_lane = getenv("PAMR_B200_NO_LANE") != nullptr;
-    const bool col_strip = tuned && tiling.Wt < W && !no_lane;
-    ForkJoin fj;
-    if (need_repack || col_strip) {
-        int rc = fj.init(dev, s);
-        if (rc != PAMR_OK) return rc;
-    }
-    const float* src = m_in;
-    int src_pitch = W;
-    int next = 0;  // next free ping-pong buffer
     int rc = PAMR_OK;
-    if (need_repack) {  // on the side stream, concurrently with the affinity / relayout kernel
-        if ((rc = fj.fork()) != PAMR_OK) return rc;
-        if ((rc = launch_repack(m_in, P[0], B * C, H, W, Wp, fj.side)) != PAMR_OK) return rc;
-        src = P[0];
-        src_pitch = Wp;
-        next = 1;
+    if (!tuned) {  // generic kernel: standard layout throughout, no side stream
+        const float* aff = aff_in;
+        if (img != nullptr) {
+            if ((rc = launch_affinity(img, aff_out, B, K, H, W, dil, tiling, s)) != PAMR_OK) return rc;
+            aff = aff_out;
+        }
+        const float* src = m_in;
+        int next = 0;
+        for (int it = 0; it < iters; ++it) {
+            const bool last = (it == iters - 1);
+            float* dst = last ? m_out : P[next];
+            if ((rc = launch_generic(aff, src, W, dst, W, B, C, H, W, dil, last ? cls_max : nullptr, s)) != PAMR_OK) return rc;
+            src = dst;
+            next ^= 1;
+        }
+        return PAMR_OK;
     }
+
+    // ---- tuned kernel: the caller's mask is repacked into the row-pair layout on the side stream,
+    //      concurrently with the affinity / relayout kernel; the column strip of every iteration runs there too
+    const bool col_strip = tiling.Wt < W;
+    ForkJoin fj;
+    if ((rc = fj.init(dev, s)) != PAMR_OK) return rc;
+    if ((rc = fj.fork()) != PAMR_OK) return rc;
+    if ((rc = launch_repack_pairs(m_in, P[0], B * C, H, W, fj.r->side)) != PAMR_OK) return rc;
     const float* aff = aff_in;
     if (img != nullptr) {
         if ((rc = launch_affinity(img, aff_out, B, K, H, W, dil, tiling, s)) != PAMR_OK) return rc;
         aff = aff_out;
-    } else if (tuned && !aff_is_tiled) {
+    } else if (!aff_is_tiled) {
         float* at = (float*)((char*)scratch + 2 * plan.pingpong_each);
         if ((rc = launch_aff_relayout(aff_in, at, B, H, W, tiling, s)) != PAMR_OK) return rc;
         aff = at;
     }
-    if (need_repack && (rc = fj.join()) != PAMR_OK) return rc;
+    if ((rc = fj.join()) != PAMR_OK) return rc;
 
     SideLane lane;
     if (col_strip) {
-        lane.stream = fj.side;
-        lane.tiles_done = fj.ev_tiles;
-        lane.strip_done = fj.ev_strip;
+        lane.stream = fj.r->side;
+        lane.tiles_done = fj.r->ev_tiles;
+        lane.strip_done = fj.r->ev_strip;
         PAMR_CUDA_TRY(cudaEventRecord(lane.tiles_done, s));  // the first strip waits for affinity / repack
+        fj.forked = true;                                    // from here on the side stream carries strip launches
     }
+    const float* src = P[0];
+    int next = 1;
+    const int Wp = pair_pitch(W);
     for (int it = 0; it < iters; ++it) {
         const bool last = (it == iters - 1);
         float* dst = last ? m_out : P[next];
-        const int dst_pitch = last ? W : Wp;
-        unsigned* mx = last ? cls_max : nullptr;
-        if (tuned) {
-            // (remainder columns / rows are computed inside the same launch, at tile boundaries)
-            rc = launch_propagate_tuned(aff, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, mx, dev, s,
-                                        col_strip ? &lane : nullptr);
-        } else {
-            rc = launch_generic(aff, src, src_pitch, dst, dst_pitch, B, C, H, W, dil, mx, s);
-        }
+        rc = launch_propagate_tuned(aff, tiling, src, dst, last ? W : Wp, !last, B, C, H, W, last ? cls_max : nullptr, dev,
+                                    s, col_strip ? &lane : nullptr);
         if (rc != PAMR_OK) return rc;
         src = dst;
-        src_pitch = dst_pitch;
         next ^= 1;
     }
     if (lane.strip_pending) PAMR_CUDA_TRY(cudaStreamWaitEvent(s, lane.strip_done, 0));  // join the last strip
+    fj.forked = false;
     return PAMR_OK;
 }
 

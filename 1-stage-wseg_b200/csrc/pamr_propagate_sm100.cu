@@ -4,23 +4,31 @@
 //   M'[b,c,y,x] = sum_{p<48} w[b,p,y,x] * M[b,c,clamp(y+dy_p),clamp(x+dx_p)]
 //
 // Design:
-//  * persistent CTAs, one per SM; a CTA owns a 32 x (4*R) pixel tile (R = 8, 9 or 10 rows per thread);
-//  * 12 compute warps in 3 groups of 4: lane = x, each thread owns a vertical strip of R pixels, so
-//    that one shared-memory load feeds up to 3*R/(R+2d) taps (register reuse along y): ~32 LDS per
-//    pixel-class instead of 48.  Group g takes the class planes c = g (mod 3);
-//  * the tile's 48 affinity weights per pixel (48*R words per thread) are read once per tile and
-//    parked in Tensor Memory (tcgen05.st), 1 TMEM lane per thread, shared by the three groups (warps
-//    w, w+4, w+8 address the same lane quarter); every class pass re-reads them with tcgen05.ld -- a
-//    data path that does not compete with LDS -- instead of holding them in registers or
-//    re-reading them through L1.  The next tile's weights are pulled into L2 with a bulk prefetch
-//    three classes before the tile boundary;
-//  * a producer warp streams the class planes of the tile (+24 px halo, 80 x (4R+48) floats)
-//    through a 4-slot shared-memory ring with TMA (cp.async.bulk.tensor.3d) + mbarriers; TMA
-//    zero-fills outside the image; replicate padding (pamr.py:50) in x is a per-lane clamped column
-//    offset, in y the consuming group patches the halo rows of top / bottom tiles before it computes;
-//  * FP32 math as packed FFMA2 over adjacent rows (a scalar FFMA with three distinct source
-//    registers issues only every ~1.8 cycles); results are stored with coalesced 128-byte rows; the
-//    per-(b,c) max for pseudo_gtmask is fused into the last iteration (warp reduce + atomicMax);
+//  * persistent CTAs, one per SM; a CTA owns a 32 x (4*R) pixel tile (R = 8 or 10 rows per thread);
+//  * 12 compute warps in 3 groups of 4: lane = x, each thread owns a vertical strip of R pixels, so that
+//    one shared-memory load feeds up to 3 taps (register reuse along y).  Group g takes the class planes
+//    c = g (mod 3);
+//  * the mask planes between iterations live in a ROW-PAIR INTERLEAVED layout [plane][y/2][x][y&1]
+//    (this library owns the ping-pong buffers), so that a thread's vertical strip is read with 64-bit
+//    shared-memory loads: LDS.64 reaches the 128 B/clk/SM of the shared-memory pipe with 8 warps where
+//    LDS.32 needs 16 and then tops out at ~92 % (profiles/r01_ubench_lds_ffma_l2.txt), the loaded pairs
+//    are the aligned register pairs the packed FFMA2 wants, and the LSU issues half the instructions;
+//  * the tile's 48 affinity weights per pixel (48*R words per thread) are parked in Tensor Memory,
+//    1 TMEM lane per thread, shared by the three groups (warps w, w+4, w+8 address the same lane
+//    quarter); every class pass re-reads them with tcgen05.ld, a data path that does not compete with
+//    LDS.  The NEXT tile's weights are streamed in behind the last class passes of the current tile by
+//    the copy engines alone, 32 TMEM columns ("unit", 16 KB for the 128 lanes) at a time and in the order
+//    the passes consume them: a loader thread brings the unit from L2 into a shared-memory staging ring
+//    with cp.async.bulk, and an issuer thread moves it on with tcgen05.cp (UTCCP: shared memory -> TMEM) as
+//    soon as the twelve compute warps have read the unit for the last time (mbarrier `free`); tcgen05.commit
+//    signals the mbarrier `filled` the first class pass of the next tile waits on, per unit.  No compute warp
+//    touches the weights on their way in, no LSU instruction is spent on them, and there is no tile-wide barrier;
+//  * a producer warp streams the class planes of the tile (+24 px halo, 80 x (4R+48) floats) through a
+//    4-slot shared-memory ring with TMA (cp.async.bulk.tensor.3d over 64-bit elements = row pairs) +
+//    mbarriers; TMA zero-fills outside the image; replicate padding (pamr.py:50) in x is a per-lane
+//    clamped column offset, in y the consuming group patches the halo rows of top / bottom tiles;
+//  * FP32 math as packed FFMA2 over adjacent rows; the per-(b,c) max for pseudo_gtmask is fused into
+//    the last iteration (warp reduce + atomicMax);
 //  * remainders of at most 8 rows / columns (W = H = 321): the row strip is computed by the CTAs that
 //    are idle in the tile kernel's last wave (or a small launch when there are none), the column strip
 //    by a small kernel on a second stream, concurrently with the tile kernel.
@@ -39,7 +47,8 @@ namespace {
 
 constexpr int TX = 32;
 constexpr int HALO = 24;
-constexpr int WIN_W = TX + 2 * HALO;  // 80 floats = 320 B rows in shared memory
+constexpr int WIN_W = TX + 2 * HALO;  // 80 columns
+constexpr int ROWP = WIN_W * 2;       // floats per row PAIR of the window in shared memory
 constexpr int NW = 4;                 // warps per compute group (= TMEM lane quarters)
 constexpr int NG = 3;                 // compute groups that share the tile's weights in TMEM (class c -> group c % NG)
 constexpr int NWC = NG * NW;          // compute warps
@@ -47,18 +56,22 @@ constexpr int NSLOT = 4;              // class-plane slots in the shared-memory 
 // mbarriers of the ring: sequence number n uses slot n % NSLOT but barrier pair n % NBAR.  Waits are by
 // phase PARITY, which is only sound if a waiter can never be a whole phase ahead of the barrier.  With one
 // barrier per slot and 4 slots, a group that has finished class k-3 tests the barrier of class k while the
-// load of class k-4 (same slot, other group) may -- once in ~1e7 passes, when that load straggles -- still
-// be in flight; the parity test then reports the OLD phase as "complete" and the group computes on the wrong
-// plane (measured: 0.2-2.5 % of the forward calls had one wrong tile-class; 0 of 2500 with 8 slots).  Eight
-// barrier pairs put 8 sequence numbers between two uses of a barrier, as in the 8-slot ring.
+// load of class k-4 (same slot, other group) may -- once in ~1e7 passes -- still be in flight; the parity
+// test then reports the OLD phase as complete and the group computes on the wrong plane (round 1: 0.2-2.5 %
+// of the forward calls had one wrong tile-class; 0 of 5500 with 8 barrier pairs).
 constexpr int NBAR = 8;
 static_assert(NBAR % NSLOT == 0 && NBAR >= 2 * NSLOT, "barrier ring must cover at least two uses of every slot");
-#ifndef PAMR_CC
-#define PAMR_CC 1
-#endif
-constexpr int CC = PAMR_CC;           // class planes per compute pass
-constexpr int NTHREADS = (NWC + 1) * 32;
-constexpr int WB = 16;                // weights per tcgen05.ld batch
+// Warp roles: 0..11 compute, 12 class-plane producer (TMA), 13 weight loader (cp.async.bulk into the staging
+// ring), 14 and 15 weight issuers (tcgen05.cp staging -> TMEM; even / odd units).
+constexpr int W_PRODUCER = NWC, W_LOADER = NWC + 1, W_ISSUER = NWC + 2;
+constexpr int NTHREADS = (NWC + 4) * 32;
+constexpr int NSTG = 6;               // staging ring for the weights: NSTG units of 16 KB ...
+constexpr int NPAIR = NSTG / 2;       // ... managed as pair-stages of two consecutive units
+constexpr int WB = 16;                // weights per tcgen05.ld batch of the centre column
+constexpr int UNIT = 32;              // TMEM columns per fill unit (= 2 batches)
+constexpr int UNIT_BYTES = UNIT * 128 * 4;  // 128 TMEM lanes
+constexpr int MAX_UNITS = 16;
+constexpr int CTRL_BYTES = 1024;
 
 __host__ __device__ constexpr int dil_of(int id) { return id == 0 ? 1 : id == 1 ? 2 : id == 2 ? 4 : id == 3 ? 8 : id == 4 ? 12 : 24; }
 
@@ -74,7 +87,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// non-blocking poll (try_wait may suspend the thread for a while before answering)
+// non-blocking poll
 __device__ __forceinline__ bool mbar_poll(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -86,12 +99,12 @@ __device__ __forceinline__ bool mbar_poll(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Blocking wait: try_wait with a suspend-time hint, so that the waiting thread sleeps in hardware until
-// the phase completes instead of re-issuing try_wait / branch pairs that take issue slots from the
-// compute warps on its scheduler (producer warp, measured per launch: 4.15 M spin iterations without
-// the hint, 0.31 M with it).
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
+// Blocking wait: try_wait with a suspend-time hint, so that the waiting thread sleeps in hardware until the
+// phase completes instead of re-issuing try_wait / branch pairs that take issue slots from the compute warps
+// on its scheduler.  A wait that does not complete within ~1e6 retries (seconds) is a protocol bug: trap
+// instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -100,6 +113,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
             : "=r"(ok)
             : "r"(bar), "r"(parity), "r"(20000u)
             : "memory");
+        if (ok == 0 && ++spins > (1u << 20)) __trap();
     } while (ok == 0);
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
@@ -108,12 +122,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
         : "memory");
 }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
-#ifdef PAMR_BODY_NO_TMEM
-    for (int j = 0; j < 16; ++j) r[j] = __uint_as_float(taddr + j) * 1e-30f;
-    return;
-#endif
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
@@ -123,119 +135,123 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
 // tcgen05.wait::ld, with the batch's registers tied through the asm so that no consumer of the
 // loaded values can be scheduled above the wait.
 __device__ __forceinline__ void tmem_wait_ld(float (&r)[16]) {
-#ifdef PAMR_BODY_NO_TMEM
-    return;
-#endif
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
                    "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]));
+}
+// plain bulk copy global -> shared memory, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// Shared-memory matrix descriptor for tcgen05.cp, no swizzle: 128 rows (= TMEM lanes) of 16-byte pieces;
+// row r, piece k (4 columns each) sits at start + (r/8)*sbo + k*lbo + (r%8)*16 (measured: tools/utccp_test.cu).
+__device__ __forceinline__ uint64_t utccp_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46);
+}
+// 128 lanes x 8 columns (two 16-byte pieces per lane) from shared memory to TMEM, asynchronously
+__device__ __forceinline__ void utccp_128x256b(uint32_t taddr, uint64_t desc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
+}
+// the mbarrier receives one arrival once every tcgen05.cp issued by this thread so far has completed
+__device__ __forceinline__ void utccp_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 // ---------------------------------------------------------------- shared-memory layout
 template <int R>
 struct Cfg {
+    static_assert(R % 2 == 0, "row pairs: R must be even");
     static constexpr int TY = NW * R;
-    static constexpr int WIN_H = TY + 2 * HALO;
+    static constexpr int WIN_H = TY + 2 * HALO;  // even
     static constexpr int SLOT_FLOATS = WIN_W * WIN_H;
     static constexpr int SLOT_BYTES = SLOT_FLOATS * 4;
-    static constexpr size_t SMEM_BYTES = (size_t)NSLOT * SLOT_BYTES + 1024;
+    static constexpr size_t STAGE_OFF = (size_t)NSLOT * SLOT_BYTES;             // weight staging ring (1024-byte aligned)
+    static constexpr size_t CTRL_OFF = STAGE_OFF + (size_t)NSTG * UNIT_BYTES;
+    static constexpr size_t SMEM_BYTES = CTRL_OFF + CTRL_BYTES;
+    static_assert(SLOT_BYTES % 128 == 0 && STAGE_OFF % 128 == 0, "TMA / bulk destinations");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
-struct Ctrl {  // lives in the last 1 KB of dynamic shared memory
-    unsigned long long tma_bar[NBAR];
-    unsigned long long empty_bar[NBAR];
+struct Ctrl {  // lives in the last CTRL_BYTES of dynamic shared memory
+    unsigned long long tma_bar[NBAR];           // class plane landed in its slot
+    unsigned long long empty_bar[NBAR];         // class plane consumed
+    unsigned long long filled_bar[MAX_UNITS];   // the tile's weights of that unit are in TMEM (tcgen05.commit)
+    unsigned long long free_bar[MAX_UNITS];     // every compute warp has read the unit for the last time in this tile
+    unsigned long long staged_bar[NPAIR];       // the pair's 2 x 16 KB have landed in the staging ring
+    unsigned long long stage_free_bar[NPAIR];   // both units of the pair have been copied on to TMEM
     uint32_t tmem_base;
 };
+static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block");
 
 struct Params {
     const float* aff;  // tile-major affinity (pamr_common.cuh), tiles_x_aff tile columns
-    float* dst;        // [B,C,H,dst_pitch]
+    const float* src;  // source mask, row-pair layout [B*C][Hp2][src_pitch][2] (the tiles read it through TMA, the strips directly)
+    float* dst;        // dst_pair: row-pair layout [B*C][Hp2][dst_pitch][2]; else standard [B*C][H][dst_pitch]
     unsigned* cls_max; // [B,C] or nullptr
-    int stagger_cta_ns, stagger_grp_ns;  // experiment knobs (env PAMR_B200_STAGGER_CTA / _GRP)
-    int dbg_cta;       // CTA that records the timeline
-    int exp_flags;     // experiments (results invalid): 1 skip weight fill, 2 skip global stores, 4 skip halo patch, 8 skip waits
-    int pf_class;      // class index at whose TMA issue the next tile's weights are prefetched into L2 (-1: never)
-    long long* dbg;    // nullptr, or timeline buffer (debug hook pamr_debug_set_timeline): 2 x 4096 x {clock, code}
-    int dst_pitch;
+    int src_pitch, dst_pitch, dst_pair, Hp2;
+    int pf_class;      // class index at whose TMA issue the prefetch of the next tile's weights into L2 starts
     int B, C, H, W;
     int tiles_x, tiles_y, ntiles;  // tiles of this launch (tiles_x may exclude the remainder strip)
     int tiles_x_aff, tiles_y_aff;  // tile grid of the affinity layout (covers the whole image)
-    const float* src;              // source mask [B,C,H,src_pitch] (for the remainder strips; tiles come through TMA)
-    int src_pitch;
-    int Wt, Ht;                    // the tiles cover [0,Wt) x [0,Ht); the producer warp computes the remainder strips
-    int strip_items;               // number of 32-pixel strip work items (all CTAs together)
+    int Wt, Ht;                    // the tiles cover [0,Wt) x [0,Ht)
+    int strip_items;               // number of 32-pixel row-strip work items
     int tail_cta0;                 // row strip inside the tile kernel: CTAs >= tail_cta0 (one tile fewer than the
                                    // others) work through the strip_items row items after their last tile; -1: off
+#ifdef PAMR_EXPERIMENTS
+    long long* dbg;                // timeline buffer [5 streams][4096][2] = {clock64, code} or nullptr (tools/timeline.py)
+    int dbg_cta;
+#endif
 };
+
+// In-kernel timeline, compiled only into experiment builds (-DPAMR_EXPERIMENTS, tools/build_variant.sh).
+#ifdef PAMR_EXPERIMENTS
+std::atomic<long long*> g_timeline{nullptr};
+std::atomic<int> g_timeline_cta{0}, g_timeline_skip{0};
+#define PAMR_EV(stream, cond, code)                                                          \
+    do {                                                                                     \
+        if (prm.dbg != nullptr && (int)blockIdx.x == prm.dbg_cta && (cond) && ev_n < 4096) { \
+            prm.dbg[((stream) * 4096 + ev_n) * 2] = clock64();                               \
+            prm.dbg[((stream) * 4096 + ev_n) * 2 + 1] = (code);                              \
+            ++ev_n;                                                                          \
+        }                                                                                    \
+    } while (0)
+#else
+#define PAMR_EV(stream, cond, code) do { } while (0)
+#endif
+
+// element (y, x) of a plane in the row-pair layout
+__host__ __device__ __forceinline__ size_t pair_index(int pitch, int y, int x) {
+    return ((size_t)(y >> 1) * pitch + x) * 2 + (y & 1);
+}
+__device__ __forceinline__ size_t src_plane_stride(const Params& p) { return (size_t)p.Hp2 * p.src_pitch * 2; }
+__device__ __forceinline__ float* dst_pixel(const Params& p, int plane, int y, int x) {
+    return p.dst_pair ? p.dst + (size_t)plane * p.Hp2 * p.dst_pitch * 2 + pair_index(p.dst_pitch, y, x)
+                      : p.dst + ((size_t)plane * p.H + y) * p.dst_pitch + x;
+}
 
 // ---------------------------------------------------------------- TMEM weight layout
-// Per thread (= TMEM lane) the 48*R weights of its R pixels are laid out in consumption order:
-//   columns [0, 12R)            centre column (b = 0): tap sequence s = 2*id + (a>0), R rows each
-//   columns SIDE0 + 32*g ...    side group g = 6*bi + id (bi = 0: b = -1, bi = 1: b = +1):
-//                               (a+1)*R + i for a = -1,0,+1  (3R <= 30 of the 32 columns used)
-// so that every side group is one aligned tcgen05.ld.x32 and the b = -1 / b = +1 halves can share
-// one (rolled) copy of the code: the unrolled loop body must stay inside the 32 KB instruction cache.
+// Per thread (= TMEM lane) the 48*R weights of its R pixels sit in consumption order, which is the dense order
+// column = s*R + i (s = tap sequence index of pamr_common.cuh: the 12 taps of the centre column b = 0 first,
+// then the side groups g = 6*bi + id with a = -1,0,+1; i = row within the thread's strip).  The passes read
+// them as a stream of 16-column batches; a fill unit is two batches (32 columns x 128 lanes = 16 KB), which is
+// one contiguous block of the tile-major affinity layout (pamr_common.cuh) and four tcgen05.cp.128x256b.
 template <int R>
 struct TmemLayout {
-    static constexpr int RS = (R + 1) / 2 * 2;                 // columns per tap: R rounded up to even, so
-                                                               // that row pairs (i, i+1) are aligned register pairs
-    static constexpr int CPAD = (12 * RS + WB - 1) / WB * WB;  // centre columns padded to a batch
-    static constexpr int SIDE0 = CPAD;
-    static constexpr int NCOLS = CPAD + 12 * 32;              // <= 512
-    static_assert(NCOLS <= 512, "TMEM columns");
+    static constexpr int NCOLS = 48 * R;          // 480 (R = 10) or 384 (R = 8) of the 512 columns
+    static constexpr int NB = NCOLS / WB;         // batches per pass
+    static constexpr int NU = NCOLS / UNIT;       // fill units per tile
+    static_assert(NCOLS % UNIT == 0 && NCOLS <= 512, "TMEM columns");
+    static_assert(NU <= MAX_UNITS, "fill units");
 };
 
-template <int R>
-__host__ __device__ constexpr int seq_col(int s) {
-    return (s < 12) ? s * TmemLayout<R>::RS
-                    : TmemLayout<R>::SIDE0 + ((s - 12) / 3) * 32 + ((s - 12) % 3) * TmemLayout<R>::RS;
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
-#ifdef PAMR_BODY_NO_TMEM
-    for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(taddr + j) * 1e-30f;
-    return;
-#endif
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
-          "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]),
-          "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]),
-          "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld32(float (&r)[32]) {
-#ifdef PAMR_BODY_NO_TMEM
-    return;
-#endif
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
-                   "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]),
-                   "+f"(r[16]), "+f"(r[17]), "+f"(r[18]), "+f"(r[19]), "+f"(r[20]), "+f"(r[21]), "+f"(r[22]),
-                   "+f"(r[23]), "+f"(r[24]), "+f"(r[25]), "+f"(r[26]), "+f"(r[27]), "+f"(r[28]), "+f"(r[29]),
-                   "+f"(r[30]), "+f"(r[31]));
-}
-__device__ __forceinline__ void tmem_st1(uint32_t taddr, float r0) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "f"(r0));
-}
-__device__ __forceinline__ void tmem_st2(uint32_t taddr, float r0, float r1) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "f"(r0), "f"(r1));
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "f"(r[0]),
-                 "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]));
-}
-
 // ---------------------------------------------------------------- compute body
-// One pass over the 48 taps for N (<= CC) class planes resident in the ring.
-// sp[n] points at this thread's pixel (row R*warp, column lane) of plane n inside its slot,
-// i.e. slot + (R*warp + HALO)*WIN_W + lane + HALO; neighbours are immediate offsets.
 // Two FMAs on adjacent rows as one packed FFMA2 (fma.rn.f32x2).  A scalar FFMA whose three source
-// registers are all distinct issues only every ~1.8 cycles per SM sub-partition (measured,
-// tools/ubench3.cu); the packed form retires two FMAs per ~2.4 cycles.  The mov.b64 packs are
-// free when ptxas allocates the operands as aligned register pairs (TMEM batches, the row strip
-// and the accumulators all are, for even R and even row shifts).
+// registers are all distinct issues only every ~1.8 cycles per SM sub-partition (tools/ubench3.cu);
+// the packed form retires two FMAs per ~2.4 cycles.  The mov.b64 packs are free when ptxas allocates the
+// operands as aligned register pairs (TMEM batches, the LDS.64 row pairs and the accumulators all are).
 __device__ __forceinline__ void fma2(float& a0, float& a1, float w0, float w1, float v0, float v1) {
     unsigned long long A, W2, V2;
     asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
@@ -244,123 +260,147 @@ __device__ __forceinline__ void fma2(float& a0, float& a1, float w0, float w1, f
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(A) : "l"(W2), "l"(V2));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(A));
 }
+__device__ __forceinline__ void lds_pair(const float* p, float& lo, float& hi) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    lo = t.x;
+    hi = t.y;
+}
+// every group has read this unit of the weights for the last time in this tile
+__device__ __forceinline__ void signal_free(uint32_t bar, int lane) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
 
-// xg = this lane's image column, W = image width: the side columns are addressed with a per-lane
-// offset clamp(xg +- d, 0, W-1) - xg, which implements replicate padding in x for free (the offset is
-// a register either way), so only rows above / below the image ever need patching in shared memory.
-template <int R, int N>
-__device__ __forceinline__ void compute_pass(const float* (&sp)[CC], uint32_t tbase, float (&acc)[CC][R], int xg,
-                                             int W) {
+// One pass over the 48 taps for one class plane resident in the ring.
+// sp points at this thread's pixel pair row (rows R*wq, R*wq+1; column lane) inside the slot, i.e.
+// slot + ((R*wq + HALO)/2)*ROWP + (lane + HALO)*2; neighbours are immediate offsets.
+// xg = this lane's image column, W = image width: the side columns are addressed with a per-lane offset
+// clamp(xg +- d, 0, W-1) - xg, which implements replicate padding in x for free, so only rows above /
+// below the image ever need patching in shared memory.
+// filled_bar != 0: first pass of the tile, wait per unit for the fill warp (phase parity par);
+// free_bar != 0: last pass of the tile, release every unit after its last read.
+template <int R>
+__device__ __forceinline__ void compute_pass(const float* __restrict__ sp, uint32_t tbase, float (&acc)[R], int xg, int W,
+                                             uint32_t filled_bar, uint32_t free_bar, uint32_t par, int lane) {
     using L = TmemLayout<R>;
-#ifdef PAMR_NO_FFMA2
-    constexpr bool kPacked = false;
-#else
-    constexpr bool kPacked = true;  // odd R: the last row stays scalar
-#endif
-    constexpr int NCB = L::CPAD / WB;  // centre batches
-    float wc[2][WB];
-    float ws[2][32];
-    tmem_ld16(tbase, wc[0]);
+    // The weights stream through two 16-register buffers in consumption order: batch b (TMEM columns
+    // [16b, 16b+16)) lives in wb[b & 1] and belongs to fill unit b / 2.  All indices are compile-time.
+    float wb[2][WB];
+    // entering batch b (its load was issued one batch earlier): wait for it, release its unit if this was
+    // the unit's second batch, and issue the load of batch b + 1
+#define PAMR_ENTER_BATCH(b)                                                                      \
+    do {                                                                                         \
+        tmem_wait_ld(wb[(b) & 1]);                                                               \
+        if (free_bar && ((b) & 1)) signal_free(free_bar + 8 * ((b) >> 1), lane);                 \
+        if ((b) + 1 < L::NB) {                                                                   \
+            if (filled_bar && (((b) + 1) & 1) == 0) {                                            \
+                mbar_wait(filled_bar + 8 * (((b) + 1) >> 1), par);                               \
+                tc_fence_after();                                                                \
+            }                                                                                    \
+            tmem_ld16(tbase + ((b) + 1) * WB, wb[((b) + 1) & 1]);                                \
+        }                                                                                        \
+    } while (0)
+    if (filled_bar) {
+        mbar_wait(filled_bar, par);
+        tc_fence_after();
+    }
+    tmem_ld16(tbase, wb[0]);
+    int bcur = -1;  // weight batch currently held (compile-time after full unrolling)
 
-    // ---- centre column (b = 0): rows y+-d for all dilations, merged into one register strip
+    // ---- centre column (b = 0): rows y+-d for all dilations share one register strip; every row pair is
+    //      loaded once, right before the first dilation that needs it (short live ranges: the strip of
+    //      all 54 rows would not fit the register budget next to the weights)
     {
-        float v[CC][R + 2 * HALO];
-#pragma unroll
-        for (int r = -HALO; r < R + HALO; ++r) {
-            bool need = false;
-#pragma unroll
-            for (int id = 0; id < 6; ++id) {
-                const int d = dil_of(id);
-                need = need || (r >= -d && r < R - d) || (r >= d && r < R + d);
-            }
-            if (need) {
-#pragma unroll
-                for (int n = 0; n < N; ++n) v[n][r + HALO] = sp[n][r * WIN_W];
-            }
-        }
-        int bcur = -1;  // weight batch currently held (compile-time after full unrolling)
+        float v[R + 2 * HALO];
 #pragma unroll
         for (int id = 0; id < 6; ++id) {
             const int d = dil_of(id);
 #pragma unroll
+            for (int r = -HALO; r < R + HALO; r += 2) {
+                bool need = false, had = false;  // needed by this dilation / already loaded for a smaller one
+#pragma unroll
+                for (int rr = r; rr < r + 2; ++rr) {
+                    need = need || (rr >= -d && rr < R - d) || (rr >= d && rr < R + d);
+#pragma unroll
+                    for (int jd = 0; jd < 6; ++jd) {
+                        const int e = dil_of(jd);
+                        if (jd < id) had = had || (rr >= -e && rr < R - e) || (rr >= e && rr < R + e);
+                    }
+                }
+                if (need && !had) lds_pair(sp + (r / 2) * ROWP, v[r + HALO], v[r + 1 + HALO]);
+            }
+#pragma unroll
             for (int a = -1; a <= 1; a += 2) {
 #pragma unroll
                 for (int i = 0; i < R; ++i) {
-                    const bool pair = kPacked && (d % 2 == 0) && (i + 1 < R || i % 2 == 1);  // rows (i, i+1) as one FFMA2
+                    const bool pair = (d % 2 == 0);  // rows (i, i+1) as one FFMA2
                     if (pair && (i % 2 == 1)) continue;  // odd row handled with its even partner
-                    const int q = (2 * id + (a > 0 ? 1 : 0)) * L::RS + i;
-                    if (q / WB != bcur) {  // batch boundary: wait for this batch, prefetch the next one
+                    const int q = (2 * id + (a > 0 ? 1 : 0)) * R + i;
+                    if (q / WB != bcur) {
                         bcur = q / WB;
-                        tmem_wait_ld(wc[bcur & 1]);
-                        if (bcur + 1 < NCB) tmem_ld16(tbase + (bcur + 1) * WB, wc[(bcur + 1) & 1]);
-                        else tmem_ld32(tbase + L::SIDE0, ws[0]);  // first side group
+                        PAMR_ENTER_BATCH(bcur);
                     }
                     if (pair) {
-#pragma unroll
-                        for (int n = 0; n < N; ++n)
-                            fma2(acc[n][i], acc[n][i + 1], wc[bcur & 1][q % WB], wc[bcur & 1][q % WB + 1],
-                                 v[n][i + a * d + HALO], v[n][i + 1 + a * d + HALO]);
+                        fma2(acc[i], acc[i + 1], wb[bcur & 1][q % WB], wb[bcur & 1][q % WB + 1], v[i + a * d + HALO],
+                             v[i + 1 + a * d + HALO]);
                     } else {
-                        const float w = wc[bcur & 1][q % WB];
-#pragma unroll
-                        for (int n = 0; n < N; ++n) acc[n][i] = fmaf(w, v[n][i + a * d + HALO], acc[n][i]);
+                        acc[i] = fmaf(wb[bcur & 1][q % WB], v[i + a * d + HALO], acc[i]);
                     }
                 }
             }
         }
     }
-    // ---- side columns: bi = 0 (b = -1), bi = 1 (b = +1); rolled so that both share one code copy
-#pragma unroll 1
+    // ---- side columns: bi = 0 (b = -1), bi = 1 (b = +1)
+#pragma unroll
     for (int bi = 0; bi < 2; ++bi) {
         const int sgn = bi * 2 - 1;
 #pragma unroll
         for (int id = 0; id < 6; ++id) {
             const int d = dil_of(id);
-            float (&w)[32] = ws[id & 1];
-            tmem_wait_ld32(w);
-            // prefetch the next side group (the last one of b = +1 has no successor)
-            if (id < 5) tmem_ld32(tbase + L::SIDE0 + (bi * 6 + id + 1) * 32, ws[(id + 1) & 1]);
-            else if (bi == 0) tmem_ld32(tbase + L::SIDE0 + 6 * 32, ws[0]);
-            float v[CC][R + 2 * HALO];
-            const int coff = min(max(xg + sgn * d, 0), W - 1) - xg;
+            float v[R + 2 * HALO];
+            const int coff = (min(max(xg + sgn * d, 0), W - 1) - xg) * 2;
 #pragma unroll
-            for (int r = -d; r < R + d; ++r) {
-                const bool need = (r < R - d) || (r >= 0 && r < R) || (r >= d);
-                if (need) {
+            for (int r = -HALO; r < R + HALO; r += 2) {
+                bool need = false;
 #pragma unroll
-                    for (int n = 0; n < N; ++n) v[n][r + HALO] = sp[n][r * WIN_W + coff];
-                }
+                for (int rr = r; rr < r + 2; ++rr)
+                    need = need || (rr >= -d && rr < R + d && ((rr < R - d) || (rr >= 0 && rr < R) || (rr >= d)));
+                if (need) lds_pair(sp + (r / 2) * ROWP + coff, v[r + HALO], v[r + 1 + HALO]);
             }
 #pragma unroll
             for (int a = -1; a <= 1; ++a) {
 #pragma unroll
                 for (int i = 0; i < R; ++i) {
-                    const bool pair = kPacked && ((a * d) % 2 == 0) && (i + 1 < R || i % 2 == 1);  // rows (i, i+1)
+                    const bool pair = ((a * d) % 2 == 0);  // rows (i, i+1)
                     if (pair && (i % 2 == 1)) continue;
+                    const int q = (12 + 3 * (bi * 6 + id) + (a + 1)) * R + i;
+                    if (q / WB != bcur) {
+                        bcur = q / WB;
+                        PAMR_ENTER_BATCH(bcur);
+                    }
                     if (pair) {
-#pragma unroll
-                        for (int n = 0; n < N; ++n)
-                            fma2(acc[n][i], acc[n][i + 1], w[(a + 1) * L::RS + i], w[(a + 1) * L::RS + i + 1],
-                                 v[n][i + a * d + HALO], v[n][i + 1 + a * d + HALO]);
+                        fma2(acc[i], acc[i + 1], wb[bcur & 1][q % WB], wb[bcur & 1][q % WB + 1], v[i + a * d + HALO],
+                             v[i + 1 + a * d + HALO]);
                     } else {
-                        const float wv = w[(a + 1) * L::RS + i];
-#pragma unroll
-                        for (int n = 0; n < N; ++n) acc[n][i] = fmaf(wv, v[n][i + a * d + HALO], acc[n][i]);
+                        acc[i] = fmaf(wb[bcur & 1][q % WB], v[i + a * d + HALO], acc[i]);
                     }
                 }
             }
         }
     }
+#undef PAMR_ENTER_BATCH
 }
 
 template <int R>
-__device__ __forceinline__ bool needs_patch(int x0, int y0, int H, int W) {
-    (void)x0; (void)W;  // replicate padding in x is handled by the per-lane column offsets
+__device__ __forceinline__ bool needs_patch(int y0, int H) {
+    // replicate padding in x is handled by the per-lane column offsets
     return y0 < HALO || y0 + Cfg<R>::TY + HALO > H;
 }
 
-// Border tiles: TMA zero-filled everything outside the image; overwrite it with the clamped
-// (replicate-padded, pamr.py:50) value.  Window element (wy,wx) <-> image pixel (y0-24+wy, x0-24+wx).
+// Border tiles: TMA zero-filled everything outside the tensor, and for odd H the second row of the last
+// row pair is allocation padding; overwrite every window row outside the image with the clamped
+// (replicate-padded, pamr.py:50) row.  Window element (wy,wx) <-> image pixel (y0-24+wy, x0-24+wx).
 // Executed by the NW warps of the compute group that is about to read the slot (wq = warp in group).
 // Every store targets an out-of-image element and every load an in-image one, so the four warps
 // need no ordering among themselves; the caller synchronises the group afterwards.
@@ -369,35 +409,26 @@ __device__ __forceinline__ void patch_window(float* slot, int x0, int y0, int H,
     constexpr int WIN_H = Cfg<R>::WIN_H;
     const int vx0 = max(0, HALO - x0), vx1 = min(WIN_W, W - x0 + HALO);  // in-image columns [vx0, vx1)
     const int vy0 = max(0, HALO - y0), vy1 = min(WIN_H, H - y0 + HALO);  // in-image rows    [vy0, vy1)
-    // rows above / below the image: full width; the source row (first / last in-image row, columns
-    // clamped) is read once and then stored to every row this warp owns
 #pragma unroll
     for (int k = 0; k < (WIN_W + 31) / 32; ++k) {
         const int wx = 32 * k + lane;
         if (wx < WIN_W) {
             const int sx = min(max(wx, vx0), vx1 - 1);
             if (vy0 > 0) {
-                const float v = slot[vy0 * WIN_W + sx];
-                for (int wy = wq; wy < vy0; wy += NW) slot[wy * WIN_W + wx] = v;
+                const float v = slot[pair_index(WIN_W, vy0, sx)];
+                for (int wy = wq; wy < vy0; wy += NW) slot[pair_index(WIN_W, wy, wx)] = v;
             }
             if (vy1 < WIN_H) {
-                const float v = slot[(vy1 - 1) * WIN_W + sx];
-                for (int wy = vy1 + wq; wy < WIN_H; wy += NW) slot[wy * WIN_W + wx] = v;
+                const float v = slot[pair_index(WIN_W, vy1 - 1, sx)];
+                for (int wy = vy1 + wq; wy < WIN_H; wy += NW) slot[pair_index(WIN_W, wy, wx)] = v;
             }
         }
     }
 }
 
-__device__ __forceinline__ void compute_bar_sync() {  // the NWC compute warps only (named barrier 1)
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    asm volatile("bar.sync 1, %0;" ::"n"(NWC * 32) : "memory");
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-
 // Remainder strips.  The tiles cover [0,Wt) x [0,Ht); when W or H leaves a remainder of at most 8
 // pixels (W = H = 321 -> one column and one row) that remainder is not worth a tile row/column of
-// its own.  It is cut into work items of 32 pixels -- item < n_col: 32 rows of one strip column,
-// otherwise 32 columns of one strip row -- which the compute warps pick up at tile boundaries
+// its own.  The row strip is cut into work items of 32 consecutive pixels of one row of one plane
 // (one pixel per lane, neighbours and weights straight from global memory / L2, clamped coordinates).
 template <int R>
 __device__ __forceinline__ void strip_item(const Params& prm, const int Wt, int item, int lane) {
@@ -419,18 +450,19 @@ __device__ __forceinline__ void strip_item(const Params& prm, const int Wt, int 
     const bool valid = (y < H) && (x < W);
     const int yc = min(y, H - 1), xc = min(x, W - 1);
     const int b = plane / C;
-    const float* __restrict__ pl = prm.src + (size_t)plane * H * prm.src_pitch;
+    const float* __restrict__ pl = prm.src + (size_t)plane * src_plane_stride(prm);
     const AffTiling tl{R, prm.tiles_x_aff, prm.tiles_y_aff, 0, 0};
-    const float* __restrict__ wp = prm.aff + aff_tiled_index(tl, b, 0, yc, xc);
+    int wi = 0;
+    const float* __restrict__ wp = prm.aff + aff_tiled_pixel_base(tl, b, yc, xc, &wi);
     float acc = 0.f;  // one FMA chain in tap-sequence order: bit-identical to the tile kernel's result
 #pragma unroll
     for (int s = 0; s < 48; ++s) {
         const int p = seq_tap(s), d = dil_of(p >> 3), j = p & 7;
         const int yy = clampi(yc + tap_dy(j) * d, 0, H - 1);
         const int xx = clampi(xc + tap_dx(j) * d, 0, W - 1);
-        acc = fmaf(__ldg(wp + s * (R * 32)), __ldg(pl + (size_t)yy * prm.src_pitch + xx), acc);
+        acc = fmaf(__ldg(wp + aff_tiled_col_offset(s * R + wi)), __ldg(pl + pair_index(prm.src_pitch, yy, xx)), acc);
     }
-    if (valid) prm.dst[((size_t)plane * H + y) * prm.dst_pitch + x] = acc;
+    if (valid) *dst_pixel(prm, plane, y, x) = acc;
     if (prm.cls_max != nullptr) {
         const unsigned m = __reduce_max_sync(0xffffffffu, valid ? ordered_from_float(acc) : 0u);
         if (lane == 0 && m != 0u) atomicMax(prm.cls_max + plane, m);
@@ -441,16 +473,27 @@ template <int R>
 __global__ void __launch_bounds__(NTHREADS, 1)
 propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params prm) {
     using C_ = Cfg<R>;
+    using L = TmemLayout<R>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* slots = reinterpret_cast<float*>(smem_raw);
-    Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem_raw + (size_t)NSLOT * C_::SLOT_BYTES);
+    unsigned char* stage_ring = smem_raw + C_::STAGE_OFF;
+    Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem_raw + C_::CTRL_OFF);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = prm.C, H = prm.H, W = prm.W;
+    const int active_groups = C < NG ? C : NG;  // groups that have at least one class pass per tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NBAR; ++s) {
             mbar_init(smem_u32(&ctrl->tma_bar[s]), 1);
             mbar_init(smem_u32(&ctrl->empty_bar[s]), NW);  // the NW warps of the group that read the slot
+        }
+        for (int u = 0; u < MAX_UNITS; ++u) {
+            mbar_init(smem_u32(&ctrl->filled_bar[u]), 1);                  // tcgen05.commit of the issuer
+            mbar_init(smem_u32(&ctrl->free_bar[u]), NW * active_groups);   // every compute warp that reads weights
+        }
+        for (int g = 0; g < NPAIR; ++g) {
+            mbar_init(smem_u32(&ctrl->staged_bar[g]), 1);
+            mbar_init(smem_u32(&ctrl->stage_free_bar[g]), 2);  // one tcgen05.commit per issuer
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -458,68 +501,111 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctrl->tmem_base)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_fence_after();
 
     const int my_tiles = (prm.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int tiles_per_img = prm.tiles_x * prm.tiles_y;
 
-    if (warp == NWC) {
-        // ===================== producer warp: TMA issue =====================
+    // tile-major affinity layout: the 48*R*128 weights of a tile are one contiguous block
+    auto tile_weights = [&](int ti) -> const float* {
+        const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+        const int b = tile / tiles_per_img, t = tile % tiles_per_img;
+        return prm.aff + (((size_t)b * prm.tiles_y_aff + t / prm.tiles_x) * prm.tiles_x_aff + t % prm.tiles_x) * ((size_t)48 * R * 128);
+    };
+
+    if (warp == W_PRODUCER) {
+        // ===================== producer warp: TMA issue of the class planes =====================
         // Sequence number n = (tile_iter, class) -> slot n % NSLOT, barrier pair n % NBAR.  A consumer
         // group waits for tma_bar (bytes landed), patches the halo itself if the tile touches the image
         // border, computes, and releases the slot through empty_bar; the producer may refill slot
         // n % NSLOT once sequence number n - NSLOT has been released.
         const long long total = (long long)my_tiles * C;
-        int pn = 0;
+        [[maybe_unused]] int ev_n = 0;
         for (long long n_issue = 0; n_issue < total; ++n_issue) {
             const int s = (int)(n_issue % NSLOT), bi = (int)(n_issue % NBAR);
             const int ti = (int)(n_issue / C), c = (int)(n_issue % C);
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
             const int x0 = (t % prm.tiles_x) * TX, y0 = (t / prm.tiles_x) * C_::TY;
-            if (lane == 0 && n_issue >= NSLOT) {  // the previous occupant of this slot has been consumed
-                const long long prev = n_issue - NSLOT;
-                mbar_wait_sleep(smem_u32(&ctrl->empty_bar[prev % NBAR]), (uint32_t)(prev / NBAR) & 1u);
-            }
             if (lane == 0) {
+                if (n_issue >= NSLOT) {  // the previous occupant of this slot has been consumed
+                    const long long prev = n_issue - NSLOT;
+                    mbar_wait(smem_u32(&ctrl->empty_bar[prev % NBAR]), (uint32_t)(prev / NBAR) & 1u);
+                }
                 const uint32_t bar = smem_u32(&ctrl->tma_bar[bi]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive_expect_tx(bar, C_::SLOT_BYTES);
-                tma_load_3d(smem_u32(slots + (size_t)s * C_::SLOT_FLOATS), &tmap, bar, x0 - HALO, y0 - HALO, b * C + c);
-                if (prm.dbg != nullptr && (int)blockIdx.x == prm.dbg_cta && pn < 4096) {  // timeline: issue time of class n
-                    prm.dbg[(2 * 4096 + pn) * 2] = clock64();
-                    prm.dbg[(2 * 4096 + pn) * 2 + 1] = 1000 + n_issue;
-                    ++pn;
-                }
+                // 64-bit elements = row pairs: coordinates (column, row pair, plane)
+                tma_load_3d(smem_u32(slots + (size_t)s * C_::SLOT_FLOATS), &tmap, bar, x0 - HALO, (y0 - HALO) / 2, b * C + c);
+                PAMR_EV(3 + 2, false, 1000 + n_issue);
             }
             // Late in a tile, pull the NEXT tile's affinity weights (one contiguous 48*R*128-byte block
-            // per lane quarter of the tile-major layout) from HBM into L2, so that the TMEM fill at the
-            // tile boundary -- when every SM asks for its weights at once -- mostly hits L2.
-            if (c == prm.pf_class && ti + 1 < my_tiles && lane < 4) {
-                const int ntile = (int)blockIdx.x + (ti + 1) * (int)gridDim.x;
-                const int nb = ntile / tiles_per_img, nt = ntile % tiles_per_img;
-                const float* wp = prm.aff + (((((size_t)nb * prm.tiles_y_aff + nt / prm.tiles_x) * prm.tiles_x_aff +
-                                               nt % prm.tiles_x) * 4 + lane) * 48 * R) * 32;
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wp), "r"(48 * R * 32 * 4) : "memory");
+            // per lane quarter of the tile-major layout) from HBM into L2, one quarter per class, so that
+            // the fill warps' loads hit L2.
+            const int pq = c - prm.pf_class;
+            if (pq >= 0 && pq < 4 && ti + 1 < my_tiles && lane == 0) {
+                const float* wp = tile_weights(ti + 1) + (size_t)pq * (12 * R * 128);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wp), "r"(12 * R * 128 * 4) : "memory");
             }
             __syncwarp();
         }
-    } else {
+    } else if (warp == W_LOADER) {
+        // ===================== weight loader: L2 -> staging ring with cp.async.bulk =====================
+        // The tiles' units form one stream n = tile_iter * NU + unit.  Two consecutive units share a
+        // pair-stage p = (n / 2) % NPAIR of the ring and one `staged` barrier (a control thread on a saturated SM
+        // pays a few hundred cycles per mbarrier round trip, so the loop is kept to one wait per 32 KB).  A
+        // pair-stage is reusable once both tcgen05.cp sets that read it have completed: each issuer commits
+        // onto `stage_free` after its unit.
+        if (lane == 0) {
+            const int total = my_tiles * L::NU;
+            [[maybe_unused]] int ev_n = 0;
+            for (int n0 = 0; n0 < total; n0 += 2) {
+                const int m = n0 >> 1, p = m % NPAIR;
+                if (m >= NPAIR) mbar_wait(smem_u32(&ctrl->stage_free_bar[p]), (uint32_t)(m / NPAIR - 1) & 1u);
+                const int cnt = (n0 + 1 < total) ? 2 : 1;
+                const uint32_t bar = smem_u32(&ctrl->staged_bar[p]);
+                mbar_arrive_expect_tx(bar, cnt * UNIT_BYTES);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j < cnt) {
+                        const int n = n0 + j, ti = n / L::NU, u = n % L::NU;
+                        bulk_load(smem_u32(stage_ring + (size_t)(2 * p + j) * UNIT_BYTES), tile_weights(ti) + (size_t)u * (UNIT * 128),
+                                  UNIT_BYTES, bar);
+                    }
+                }
+                PAMR_EV(3, true, 2000 + (n0 % L::NU));
+            }
+        }
+    } else if (warp >= W_ISSUER) {
+        // ===================== weight issuers: staging ring -> TMEM with tcgen05.cp =====================
+        // two control threads (warps 14 and 15), even and odd units of the stream
+        if (lane == 0) {
+            const int total = my_tiles * L::NU;
+            const uint32_t tb = ctrl->tmem_base;
+            [[maybe_unused]] int ev_n = 0;
+            for (int n = warp - W_ISSUER; n < total; n += 2) {
+                const int ti = n / L::NU, u = n % L::NU, m = n >> 1, p = m % NPAIR;
+                mbar_wait(smem_u32(&ctrl->staged_bar[p]), (uint32_t)(m / NPAIR) & 1u);  // bytes landed
+                if (ti > 0) mbar_wait(smem_u32(&ctrl->free_bar[u]), (uint32_t)(ti - 1) & 1u);  // the previous tile's last passes have read the unit
+                tc_fence_after();
+                PAMR_EV(4, warp == W_ISSUER, 2100 + u);
+                const uint32_t sa = smem_u32(stage_ring + (size_t)(2 * p + (n & 1)) * UNIT_BYTES);
+#pragma unroll
+                for (int k = 0; k < UNIT / 8; ++k)  // 8 columns each: pieces 2k, 2k+1 (2 KB apart), 8-lane groups 128 B apart
+                    utccp_128x256b(tb + u * UNIT + k * 8, utccp_desc(sa + k * 4096, 2048, 128));
+                utccp_commit(smem_u32(&ctrl->filled_bar[u]));
+                utccp_commit(smem_u32(&ctrl->stage_free_bar[p]));
+            }
+            // a lone last unit has no partner: its pair-stage is never reused, nothing to balance
+        }
+    } else if (warp < NWC) {
         // ===================== compute warps: NG groups x NW warps =====================
         const int grp = warp / NW, wq = warp % NW;  // wq = TMEM lane quarter; all groups share the weights
         const uint32_t tbase = ctrl->tmem_base + ((uint32_t)(wq * 32) << 16);
-        int dn = 0;  // timeline events written by this group's leader lane of CTA 0
-        if ((blockIdx.x & 1) && prm.stagger_cta_ns > 0) __nanosleep(prm.stagger_cta_ns);
-#define PAMR_EV(code)                                                                         \
-    do {                                                                                      \
-        if (prm.dbg != nullptr && (int)blockIdx.x == prm.dbg_cta && grp < 2 && wq == 0 && lane == 0 && dn < 4096) {      \
-            prm.dbg[((grp & 1) * 4096 + dn) * 2] = clock64();                                        \
-            prm.dbg[((grp & 1) * 4096 + dn) * 2 + 1] = (code);                                       \
-            ++dn;                                                                             \
-        }                                                                                     \
-    } while (0)
+        const uint32_t filled0 = smem_u32(&ctrl->filled_bar[0]), free0 = smem_u32(&ctrl->free_bar[0]);
+        [[maybe_unused]] int ev_n = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
@@ -527,118 +613,79 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             const int x = x0 + lane, yw = y0 + wq * R;
             const bool xok = x < W;
             const long long seq0 = (long long)ti * C;
-            const bool border = needs_patch<R>(x0, y0, H, W);
-
-            // ---- park the tile's 48*R weights per thread in TMEM (layout: TmemLayout); each group
-            //      loads its share (48/NG) of the taps for the lanes it shares with its sibling warps
-            PAMR_EV(1);
-            if (ti > 0) compute_bar_sync();  // nobody still reads the previous tile's weights
-            PAMR_EV(2);
-            {
-                // tile-major layout: this thread's weights are ap[(s*R + i)*32], s = tap sequence index
-                const int ty = t / prm.tiles_x, tx = t % prm.tiles_x;
-                const float* __restrict__ ap =
-                    prm.aff + (((((size_t)b * prm.tiles_y_aff + ty) * prm.tiles_x_aff + tx) * 4 + wq) * 48 * R) * 32 + lane;
-                // FILL_TAPS*R loads are in flight before the first TMEM store: memory-level
-                // parallelism is what bounds this phase (the accumulators are not live here)
-                constexpr int TAPS_PER_GROUP = 48 / NG, FILL_TAPS = 8;
-#pragma unroll
-                for (int h = 0; h < ((prm.exp_flags & 1) ? 0 : TAPS_PER_GROUP / FILL_TAPS); ++h) {
-                    const int s0 = TAPS_PER_GROUP * grp + h * FILL_TAPS;  // grp is warp-uniform; offsets below are immediates
-                    const float* __restrict__ bp = ap + (size_t)s0 * R * 32;
-                    float r[FILL_TAPS][R];
-#pragma unroll
-                    for (int k = 0; k < FILL_TAPS; ++k)
-#pragma unroll
-                        for (int i = 0; i < R; ++i) r[k][i] = __ldg(bp + (k * R + i) * 32);
-#pragma unroll
-                    for (int k = 0; k < FILL_TAPS; ++k) {
-                        const uint32_t col = tbase + seq_col<R>(s0 + k);
-                        tmem_st8(col, r[k]);
-                        if (R == 9) tmem_st1(col + 8, r[k][R - 1]);
-                        if (R == 10) tmem_st2(col + 8, r[k][R - 2], r[k][R - 1]);
-                    }
-                }
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            }
-            PAMR_EV(3);
-            compute_bar_sync();  // both halves of the weights are visible to both groups
-            PAMR_EV(4);
-            if (grp != 0 && prm.stagger_grp_ns > 0) __nanosleep(prm.stagger_grp_ns * grp);
+            const bool border = needs_patch<R>(y0, H);
+            const int nrow = xok ? max(0, min(R, H - yw)) : 0;  // rows of this thread inside the image
 
             int probe = 0;  // 1: the barriers of this group's next class were already seen complete
             for (int k = grp; k < C; k += NG) {
-                const int c0 = k, n = 1;
                 const long long sq = seq0 + k;
                 const int s = (int)(sq % NSLOT), bi = (int)(sq % NBAR);
                 const uint32_t par = (uint32_t)(sq / NBAR) & 1u;
-                PAMR_EV(100 + k);
-                if (!probe && !(prm.exp_flags & 8)) mbar_wait_sleep(smem_u32(&ctrl->tma_bar[bi]), par);  // bytes landed
-                if (border && !(prm.exp_flags & 4)) {  // replicate padding: the group patches the halo of its own slot
-                    patch_window<R>(slots + (size_t)s * C_::SLOT_FLOATS, x0, y0, H, W, wq, lane);
+                PAMR_EV(grp, wq == 0 && lane == 0, 100 + k);
+                if (!probe) mbar_wait(smem_u32(&ctrl->tma_bar[bi]), par);  // bytes landed
+                PAMR_EV(grp, wq == 0 && lane == 0, 6);
+                float* slot = slots + (size_t)s * C_::SLOT_FLOATS;
+                if (border) {  // replicate padding: the group patches the halo rows of its own slot
+                    patch_window<R>(slot, x0, y0, H, W, wq, lane);
                     // immediate barrier ids: with a register id ptxas reserves all 16 named barriers and no
                     // other CTA (the concurrent column strip) could share the SM
                     if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(NW * 32) : "memory");
                     else if (grp == 1) asm volatile("bar.sync 3, %0;" ::"n"(NW * 32) : "memory");
                     else asm volatile("bar.sync 4, %0;" ::"n"(NW * 32) : "memory");
                 }
-                const float* sp[CC];
+                const float* sp = slot + ((wq * R + HALO) / 2) * ROWP + (lane + HALO) * 2;
+                float acc[R];
 #pragma unroll
-                for (int j = 0; j < CC; ++j)
-                    sp[j] = slots + (size_t)s * C_::SLOT_FLOATS + (wq * R + HALO) * WIN_W + lane + HALO;
-                PAMR_EV(6);
-                float acc[CC][R];
-#pragma unroll
-                for (int j = 0; j < CC; ++j)
-#pragma unroll
-                    for (int i = 0; i < R; ++i) acc[j][i] = 0.f;
-                compute_pass<R, 1>(sp, tbase, acc, x, W);
-                PAMR_EV(9);
+                for (int i = 0; i < R; ++i) acc[i] = 0.f;
+#if defined(PAMR_EXPERIMENTS) && defined(PAMR_X_NOCHASE)    // timing experiment: no weight hand-over at all (wrong values)
+                const bool first = false, last = false;
+#else
+                const bool first = (k == grp), last = (k + NG >= C);
+#endif
+                compute_pass<R>(sp, tbase, acc, x, W, first ? filled0 : 0u, last ? free0 : 0u, (uint32_t)ti & 1u, lane);
+                PAMR_EV(grp, wq == 0 && lane == 0, 9);
                 // release the slot as early as possible
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&ctrl->empty_bar[bi]));
-                // Probe the next class's barriers now, without blocking: an mbarrier test takes a few
-                // hundred cycles when the LSU queues are full of LDS, and that latency then overlaps the
-                // stores below instead of sitting at the head of the next pass.
+                // Probe the next class's barrier now, without blocking: its latency overlaps the stores below
+                // instead of sitting at the head of the next pass.
                 probe = 0;
                 if (k + NG < C) {
                     const long long sq2 = sq + NG;
-                    const uint32_t par2 = (uint32_t)(sq2 / NBAR) & 1u;
-                    probe = (int)mbar_poll(smem_u32(&ctrl->tma_bar[sq2 % NBAR]), par2);
+                    probe = (int)mbar_poll(smem_u32(&ctrl->tma_bar[sq2 % NBAR]), (uint32_t)(sq2 / NBAR) & 1u);
                 }
-                PAMR_EV(7);
-                // ---- store (coalesced 128 B per row) and optional class max
+                // ---- store and optional class max
+                const int plane = b * C + k;
+                if (prm.dst_pair) {  // row pairs: 8-byte stores, 256 contiguous bytes per warp
+                    float2* __restrict__ op = reinterpret_cast<float2*>(prm.dst) +
+                                              ((size_t)plane * prm.Hp2 + (yw >> 1)) * prm.dst_pitch + x;
+                    const size_t pitch = (size_t)prm.dst_pitch;
 #pragma unroll
-                for (int j = 0; j < CC; ++j) {
-                    if (j < n) {
-                        float* __restrict__ op = prm.dst + ((size_t)(b * C + c0 + j) * H + yw) * prm.dst_pitch + x;
-                        const int nrow = xok ? min(R, H - yw) : 0;  // rows of this thread inside the image
-                        if (!(prm.exp_flags & 2)) {
-                            // running pointer: one 64-bit add per row instead of a 64-bit multiply-add chain
-                            const size_t pitch = (size_t)prm.dst_pitch;
-                            if (nrow == R) {
+                    for (int i = 0; i < R; i += 2, op += pitch)
+                        if (i < nrow) *op = make_float2(acc[i], acc[i + 1]);  // (odd H: row H lands in the allocation padding)
+                } else {  // last iteration: the caller's [B,C,H,W] tensor, coalesced 128-byte rows
+                    float* __restrict__ op = prm.dst + ((size_t)plane * H + yw) * prm.dst_pitch + x;
+                    const size_t pitch = (size_t)prm.dst_pitch;
+                    if (nrow == R) {
 #pragma unroll
-                                for (int i = 0; i < R; ++i, op += pitch) *op = acc[j][i];
-                            } else {
+                        for (int i = 0; i < R; ++i, op += pitch) *op = acc[i];
+                    } else {
 #pragma unroll
-                                for (int i = 0; i < R; ++i, op += pitch)
-                                    if (i < nrow) *op = acc[j][i];
-                            }
-                        }
-                        if (prm.cls_max != nullptr) {  // last iteration only: keep its ALU work out of the other nine
-                            unsigned mx = 0u;
-#pragma unroll
-                            for (int i = 0; i < R; ++i)
-                                if (i < nrow) mx = max(mx, ordered_from_float(acc[j][i]));
-                            mx = __reduce_max_sync(0xffffffffu, mx);
-                            if (lane == 0 && mx != 0u) atomicMax(prm.cls_max + (size_t)b * C + c0 + j, mx);
-                        }
+                        for (int i = 0; i < R; ++i, op += pitch)
+                            if (i < nrow) *op = acc[i];
                     }
                 }
-                PAMR_EV(8);
+                if (prm.cls_max != nullptr) {  // last iteration only: keep its ALU work out of the other nine
+                    unsigned mx = 0u;
+#pragma unroll
+                    for (int i = 0; i < R; ++i)
+                        if (i < nrow) mx = max(mx, ordered_from_float(acc[i]));
+                    mx = __reduce_max_sync(0xffffffffu, mx);
+                    if (lane == 0 && mx != 0u) atomicMax(prm.cls_max + plane, mx);
+                }
+                PAMR_EV(grp, wq == 0 && lane == 0, 8);
             }
         }
-#undef PAMR_EV
         // ---- row strip in the tail: the CTAs that own one tile fewer than the rest would idle during
         //      the last wave; they compute the row strip y in [Ht,H) instead (no separate launch)
         if (prm.tail_cta0 >= 0 && (int)blockIdx.x >= prm.tail_cta0) {
@@ -648,16 +695,16 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         }
     }
 
+    tc_fence_before();
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(ctrl->tmem_base), "r"(512));
 }
 
 // ---- remainder strips as small kernels (row strip: only when the tile kernel's last wave has no idle CTAs) ----
-// (Alternatives measured on B200 and rejected: the same work inside the persistent kernel by the
-//  producer warp -- its ~100 global loads per item queue behind the compute warps' LDS traffic -- or by
-//  the compute warps at every tile boundary -- it lengthens every boundary; the remainder column fused
-//  into the last full tile column -- a bank-conflicted extra pass; partial tiles cost a whole tile column.)
+// (Alternatives measured on B200 in round 1 and rejected: the same work inside the persistent kernel by the
+//  producer warp or by the compute warps at every tile boundary; the remainder column fused into the last
+//  full tile column -- a bank-conflicted extra pass; partial tiles cost a whole tile column.)
 
 // Row strip: y in [Ht,H), all x.  One warp per 32 consecutive pixels of a row (coalesced).
 template <int R>
@@ -668,14 +715,15 @@ __global__ void __launch_bounds__(128) strip_rows_kernel(const Params prm) {
 }
 
 // Column strip: x in [Wt,W), all y.  Neighbours of a column of pixels lie in different rows, i.e.
-// in different cache lines, so one CTA stages the last 24 + (W-Wt) columns of 32 + 48 rows of all C
-// class planes in shared memory with coalesced row reads (one warp per class plane), then every
-// warp computes 32 pixels (lane = row) x (W-Wt) columns of its class from shared memory.
+// in different cache lines, so one CTA stages the last 32 columns of 32 + 48 rows of the class planes in
+// shared memory with coalesced row reads (one warp per class plane), then every warp computes 32 pixels
+// (lane = row) x (W-Wt) columns of its class from shared memory.
 constexpr int SC_ROWS = 32;                      // pixel rows per CTA
 constexpr int SC_WIN_H = SC_ROWS + 2 * HALO;     // 80
 constexpr int SC_WIN_W = 32;                     // staged columns [W-32, W)  (needs W >= 32)
 constexpr int SC_LOADS = 20;                     // row loads in flight per thread while staging (SC_WIN_H % SC_LOADS == 0)
 constexpr int SC_CG = 8;                         // class planes staged at a time (one warp each)
+constexpr int SC_MAX_WC = 8;                     // widest column strip (shared-memory weights, window columns)
 template <int R>
 __global__ void __launch_bounds__(SC_CG * 32, 5) strip_cols_kernel(const Params prm) {  // (.,5): <= 48 registers, so that a CTA fits next to a resident tile CTA
     extern __shared__ float sc_smem[];  // [SC_CG][SC_WIN_H][SC_WIN_W + 1] then weights [wc][48][32]
@@ -696,16 +744,15 @@ __global__ void __launch_bounds__(SC_CG * 32, 5) strip_cols_kernel(const Params 
     for (int c0 = 0; c0 < C; c0 += SC_CG) {
         const int c = c0 + warp;
         if (c < C) {  // stage this warp's class plane window (rows clamped: replicate padding)
-            const float* __restrict__ pl = prm.src + ((size_t)b * C + c) * H * prm.src_pitch;
+            const float* __restrict__ pl = prm.src + ((size_t)b * C + c) * src_plane_stride(prm);
             // SC_LOADS row loads in flight at a time: the kernel overlaps the tile kernel on a second stream and is
-            // kept at <= 48 registers so that its CTAs can be placed next to a resident tile CTA (12 K registers
-            // are free there).  321x321 B=16 forward: 8 loads 2.83 ms, 16: 2.82, 20: 2.77, 40 (64 registers): 2.80
+            // kept at <= 48 registers so that its CTAs can be placed next to a resident tile CTA
 #pragma unroll 1
             for (int r0 = 0; r0 < SC_WIN_H; r0 += SC_LOADS) {
                 float v[SC_LOADS];
 #pragma unroll
                 for (int q = 0; q < SC_LOADS; ++q)
-                    v[q] = __ldg(pl + (size_t)clampi(yb - HALO + r0 + q, 0, H - 1) * prm.src_pitch + xs0 + lane);
+                    v[q] = __ldg(pl + pair_index(prm.src_pitch, clampi(yb - HALO + r0 + q, 0, H - 1), xs0 + lane));
 #pragma unroll
                 for (int q = 0; q < SC_LOADS; ++q) mywin[(r0 + q) * PITCH + lane] = v[q];
             }
@@ -714,7 +761,7 @@ __global__ void __launch_bounds__(SC_CG * 32, 5) strip_cols_kernel(const Params 
         if (c < C) {
             const float* win = mywin + (lane + HALO) * PITCH;
             for (int xi = 0; xi < wc; ++xi) {
-                const int xl = prm.Wt + xi - xs0;  // column inside the staged window
+                const int xl = prm.Wt + xi - xs0;  // column inside the staged window (>= 24: wc <= SC_MAX_WC)
                 float acc = 0.f;  // tap-sequence order, like the tile kernel (bit-identical results)
 #pragma unroll
                 for (int sq = 0; sq < 48; ++sq) {
@@ -723,7 +770,7 @@ __global__ void __launch_bounds__(SC_CG * 32, 5) strip_cols_kernel(const Params 
                     acc = fmaf(wsm[(xi * 48 + sq) * SC_ROWS + lane], win[tap_dy(j) * d * PITCH + xx], acc);
                 }
                 const bool valid = y < H;
-                if (valid) prm.dst[(((size_t)b * C + c) * H + y) * prm.dst_pitch + prm.Wt + xi] = acc;
+                if (valid) *dst_pixel(prm, b * C + c, y, prm.Wt + xi) = acc;
                 if (prm.cls_max != nullptr) {
                     const unsigned m = __reduce_max_sync(0xffffffffu, valid ? ordered_from_float(acc) : 0u);
                     if (lane == 0 && m != 0u) atomicMax(prm.cls_max + (size_t)b * C + c, m);
@@ -734,17 +781,19 @@ __global__ void __launch_bounds__(SC_CG * 32, 5) strip_cols_kernel(const Params 
     }
 }
 
-// Copy [planes,H,W] -> [planes,H,Wp] (Wp % 4 == 0) so that TMA's 16-byte stride rule holds.
-__global__ void repack_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int Wp, size_t rows) {
-    for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
-        const float* __restrict__ s = src + row * W;
-        float* __restrict__ d = dst + row * Wp;
-        for (int x = threadIdx.x; x < W; x += blockDim.x) d[x] = s[x];
+// Copy [planes,H,W] -> row-pair layout [planes,Hp2,Wp,2] (TMA reads 64-bit elements; Wp even keeps its
+// global strides multiples of 16 bytes).  For odd H the second row of the last pair repeats row H-1.
+__global__ void __launch_bounds__(128) repack_pairs_kernel(const float* __restrict__ src, float2* __restrict__ dst, int H, int W,
+                                                           int Hp2, int Wp, size_t pair_rows) {
+    for (size_t pr = blockIdx.x; pr < pair_rows; pr += gridDim.x) {
+        const size_t plane = pr / Hp2;
+        const int p = (int)(pr % Hp2);
+        const float* __restrict__ s0 = src + (plane * H + 2 * p) * W;
+        const float* __restrict__ s1 = src + (plane * H + min(2 * p + 1, H - 1)) * W;
+        float2* __restrict__ d = dst + pr * Wp;
+        for (int x = threadIdx.x; x < W; x += blockDim.x) d[x] = make_float2(__ldg(s0 + x), __ldg(s1 + x));
     }
-    (void)H;
 }
-
-std::atomic<long long*> g_timeline{nullptr};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -763,14 +812,15 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int make_tmap(CUtensorMap* map, const float* base, int planes, int H, int W, int pitch, int win_h) {
+// 3-D map over 64-bit elements (one element = the two rows of a row pair at one column)
+int make_tmap(CUtensorMap* map, const float* base, int planes, int Hp2, int Wp, int win_h) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) return set_error(PAMR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
-    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * 4 * (cuuint64_t)H};
-    cuuint32_t box[3] = {(cuuint32_t)WIN_W, (cuuint32_t)win_h, 1};
+    cuuint64_t dims[3] = {(cuuint64_t)Wp, (cuuint64_t)Hp2, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)Wp * 8, (cuuint64_t)Wp * 8 * (cuuint64_t)Hp2};
+    cuuint32_t box[3] = {(cuuint32_t)WIN_W, (cuuint32_t)(win_h / 2), 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<float*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(PAMR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -781,92 +831,89 @@ int make_tmap(CUtensorMap* map, const float* base, int planes, int H, int W, int
 // tile in that wave take the row-strip items (one warp per item, ~2.5 us each, TAIL_ITEMS_MAX in a
 // row still fit inside one tile time); otherwise the strip is a launch of its own.
 constexpr int TAIL_ITEMS_MAX = 8;
-inline bool row_strip_in_tail(long long items, int ntiles, int grid) {
-    static const bool off = getenv("PAMR_B200_NO_TAIL") != nullptr;
-    if (off || grid <= 0 || ntiles <= grid || ntiles % grid == 0) return false;
+inline bool row_strip_in_tail(long long items, long long ntiles, int grid) {
+    if (grid <= 0 || ntiles <= grid || ntiles % grid == 0) return false;
     const long long warps = (long long)(grid - ntiles % grid) * NWC;
     return (items + warps - 1) / warps <= TAIL_ITEMS_MAX;
 }
 
+int device_sm_count(int dev, int* out) {
+    static std::atomic<int> cache[64];
+    int n = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
+    if (n == 0) {
+        PAMR_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
+    }
+    *out = n;
+    return PAMR_OK;
+}
+
 template <int R>
 int launch_one(const float* aff, const AffTiling& tiling, const float* src, int src_pitch, float* dst, int dst_pitch,
-               int B, int C, int H, int W, int Wt, int Ht, unsigned* cls_max, int sm_count, cudaStream_t s,
-               SideLane* lane) {
+               bool dst_pair, int B, int C, int H, int W, int Wt, int Ht, unsigned* cls_max, int sm_count, int dev,
+               cudaStream_t s, SideLane* lane) {
     using C_ = Cfg<R>;
     // function attributes are per device: set once per (kernel, device)
     static std::atomic<int> attr_set[64];
-    int dev = 0;
-    PAMR_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev >= 64 || attr_set[dev].load(std::memory_order_acquire) == 0) {
+    if (dev < 0 || dev >= 64 || attr_set[dev].load(std::memory_order_acquire) == 0) {
         PAMR_CUDA_TRY(cudaFuncSetAttribute(propagate_sm100_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)C_::SMEM_BYTES));
-        if (dev < 64) attr_set[dev].store(1, std::memory_order_release);
+        PAMR_CUDA_TRY(cudaFuncSetAttribute(strip_cols_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        if (dev >= 0 && dev < 64) attr_set[dev].store(1, std::memory_order_release);
     }
+    const int Hp2 = (H + 1) / 2;
     alignas(64) CUtensorMap tmap;
-    int rc = make_tmap(&tmap, src, B * C, H, W, src_pitch, C_::WIN_H);
+    int rc = make_tmap(&tmap, src, B * C, Hp2, src_pitch, C_::WIN_H);
     if (rc != PAMR_OK) return rc;
     Params p;
-    p.aff = aff; p.dst = dst; p.cls_max = cls_max; p.dst_pitch = dst_pitch;
-    p.dbg = g_timeline.load(std::memory_order_relaxed);
-    static const int knob_cta = getenv("PAMR_B200_STAGGER_CTA") ? atoi(getenv("PAMR_B200_STAGGER_CTA")) : 0;
-    // groups 1 and 2 start their first pass of a tile 0.5 / 1.0 us after group 0: keeps the three groups out of
-    // phase, so that one group's wait -> release -> store latency overlaps the others' LDS-bound passes
-    // (320x320 B=16 forward: 2.541 ms without, 2.522 / 2.511 / 2.517 ms with 200 / 500 / 1000 ns)
-    static const int knob_grp = getenv("PAMR_B200_STAGGER_GRP") ? atoi(getenv("PAMR_B200_STAGGER_GRP")) : 500;
-    p.stagger_cta_ns = knob_cta; p.stagger_grp_ns = knob_grp;
-    // default: prefetch the next tile's weights when the third-last class is issued (PAMR_B200_PF_CLASS overrides)
-    static const int knob_pf = getenv("PAMR_B200_PF_CLASS") ? atoi(getenv("PAMR_B200_PF_CLASS")) : -2;
-    p.pf_class = (knob_pf == -2) ? (C >= 3 ? C - 3 : 0) : (knob_pf < C ? knob_pf : -1);
-    p.dbg_cta = getenv("PAMR_B200_DBG_CTA") ? atoi(getenv("PAMR_B200_DBG_CTA")) : 0;
-    p.exp_flags = getenv("PAMR_B200_EXPERIMENT") ? atoi(getenv("PAMR_B200_EXPERIMENT")) : 0;
+    p.aff = aff; p.src = src; p.dst = dst; p.cls_max = cls_max;
+    p.src_pitch = src_pitch; p.dst_pitch = dst_pitch; p.dst_pair = dst_pair ? 1 : 0; p.Hp2 = Hp2;
+    p.pf_class = C >= 8 ? C - 8 : 0;
     p.B = B; p.C = C; p.H = H; p.W = W;
     p.tiles_x = (Wt + TX - 1) / TX;
     p.tiles_y = (Ht + C_::TY - 1) / C_::TY;
     p.tiles_x_aff = tiling.tiles_x;
     p.tiles_y_aff = tiling.tiles_y;
-    p.src = src; p.src_pitch = src_pitch; p.Wt = Wt; p.Ht = Ht;
+    p.Wt = Wt; p.Ht = Ht;
     p.strip_items = 0;
     p.tail_cta0 = -1;
-    p.ntiles = p.tiles_x * p.tiles_y * B;
+#ifdef PAMR_EXPERIMENTS
+    p.dbg = nullptr;
+    p.dbg_cta = g_timeline_cta.load(std::memory_order_relaxed);
+    if (g_timeline.load() != nullptr && g_timeline_skip.fetch_sub(1) == 0) p.dbg = g_timeline.exchange(nullptr);  // record one launch
+#endif
+    const long long ntiles = (long long)p.tiles_x * p.tiles_y * B;
+    if (ntiles > 0x7fffffffLL) return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: too many tiles");
+    p.ntiles = (int)ntiles;
     const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
-    const bool skip_strips = getenv("PAMR_B200_EXPERIMENT") && (atoi(getenv("PAMR_B200_EXPERIMENT")) & 16);
-    const bool col_strip = Wt < W && !skip_strips;
+    const bool col_strip = Wt < W;
     if (col_strip && lane != nullptr && lane->strip_pending) {  // this iteration reads what strip(t-1) wrote
         PAMR_CUDA_TRY(cudaStreamWaitEvent(s, lane->strip_done, 0));
         lane->strip_pending = false;
     }
     const long long row_items = (long long)B * C * (H - Ht) * ((W + 31) / 32);
     if (row_items > 0x7fffffffLL) return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: row strip too large");
-    if (Ht < H && !skip_strips && row_strip_in_tail(row_items, p.ntiles, grid)) {
+    if (Ht < H && row_strip_in_tail(row_items, ntiles, grid)) {
         p.strip_items = (int)row_items;  // the tile kernel's short CTAs do the row strip
         p.tail_cta0 = p.ntiles % grid;
-    } else if (Ht < H && !skip_strips) {  // row strip y in [Ht,H), all columns, as a launch of its own
+    } else if (Ht < H) {  // row strip y in [Ht,H), all columns, as a launch of its own
         Params pr = p;
         pr.Wt = W;  // strip_item: no column part, the row part spans [0,W)
         pr.strip_items = (int)row_items;
-        const long long items = row_items;
-        const int blocks = (int)((items + 3) / 4);
+        const int blocks = (int)((row_items + 3) / 4);
         strip_rows_kernel<R><<<blocks < 8 * sm_count ? blocks : 8 * sm_count, 128, 0, s>>>(pr);
         count_launch();
         PAMR_CUDA_TRY(cudaGetLastError());
     }
     // The column strip (x in [Wt,W), all rows) runs on the side lane concurrently with the tile kernel:
-    // both only read iteration t-1.  Measured on B200 its CTAs mostly get placed as tile CTAs retire in
-    // the last wave (side-stream CTAs are scheduled only sluggishly next to resident persistent CTAs,
-    // tools/coresidency.py), which still hides about half of it: 321x321 B=16 forward 3.085 ms vs
-    // 3.204 ms with the strip serialised.  Ordering: the main stream waited for strip(t-1) above
+    // both only read iteration t-1.  Its CTAs mostly get placed as tile CTAs retire in the last wave,
+    // which hides about half of it.  Ordering: the main stream waited for strip(t-1) above
     // (iteration t reads and overwrites what that strip wrote / read); strip(t) waits for tiles(t-1).
-    Params pm = p;
-    propagate_sm100_kernel<R><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, pm);
+    propagate_sm100_kernel<R><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, p);
     count_launch();
     PAMR_CUDA_TRY(cudaGetLastError());
     if (col_strip) {
         const size_t smem = sizeof(float) * ((size_t)SC_CG * SC_WIN_H * (SC_WIN_W + 1) + (size_t)(W - Wt) * 48 * SC_ROWS);
-        static std::atomic<int> sc_attr[64];
-        if (dev >= 64 || sc_attr[dev].load(std::memory_order_acquire) == 0) {
-            PAMR_CUDA_TRY(cudaFuncSetAttribute(strip_cols_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            if (dev < 64) sc_attr[dev].store(1, std::memory_order_release);
-        }
         dim3 sgrid((H + SC_ROWS - 1) / SC_ROWS, B);
         cudaStream_t ss = s;
         if (lane != nullptr) {
@@ -887,9 +934,15 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
 
 }  // namespace
 
-// Debug hook (not part of the public ABI): device buffer of 2 x 4096 x 2 int64 that CTA 0 of every
-// subsequent tuned launch fills with {clock64, event code} pairs; nullptr switches it off.
-extern "C" void pamr_debug_set_timeline(long long* dev_buf) { g_timeline.store(dev_buf); }
+#ifdef PAMR_EXPERIMENTS
+// Debug hook of experiment builds only (not part of the ABI): device buffer of 5 x 4096 x 2 int64 that CTA `cta`
+// of ONE tuned launch (after skipping `skip` launches) fills with {clock64, event code} pairs.
+extern "C" void pamr_debug_set_timeline(long long* dev_buf, int cta, int skip) {
+    g_timeline_cta.store(cta);
+    g_timeline_skip.store(skip);
+    g_timeline.store(dev_buf);
+}
+#endif
 
 // Tiling of the tuned kernel (R rows per thread, tile = 32 x 4R, extent [0,Wt) x [0,Ht) covered by
 // tiles) or R == 0 when the tuned kernel does not apply.  Remainders of at most 8 rows / columns have
@@ -897,45 +950,34 @@ extern "C" void pamr_debug_set_timeline(long long* dev_buf) { g_timeline.store(d
 //   rows:    the row strip -- inside the tile kernel's last wave when that wave has idle CTAs
 //            (row_strip_in_tail), else a launch of its own;
 //   columns: the column-strip launch.
-// All combinations with R in {8,9,10} are priced with a time model fitted to measurements on B200
-// (profiles/r01_strip_times.txt): waves of tiles over the SMs at ~2.8 us per row-per-thread, row-strip
-// launch ~ 8 + 1.3 us per 1000 items, column-strip launch ~ (12 + 2.6 wc) * max(1, CTAs/90)^0.8 us minus what
-// hides in the last wave -- and the cheapest wins.  E.g. 321 x 321, B=16: R=10, 10 x 8 tiles, row 320 in the
-// tail of the same launch, column 320 as a strip launch on the side lane.  All paths add the 48 products of a pixel in the same order, so the result
-// does not depend on the tiling (nor, therefore, on how a batch is sharded).
-// Experiment overrides: PAMR_B200_ROWS=8|9|10, PAMR_B200_STRIP_MAX=<pixels> (0 disables strips),
-// PAMR_B200_FORCE_STRIPS (bit 0 rows, bit 1 columns: take the strip whenever it qualifies),
-// PAMR_B200_NO_TAIL=1.
+// All combinations with R in {8,10} are priced with a time model fitted to measurements on B200
+// (profiles/r01_strip_times.txt): waves of tiles over the SMs at a cost per row-per-thread, row-strip
+// launch ~ 8 + 1.3 us per 1000 items, column-strip launch ~ (12 + 2.6 wc) * max(1, CTAs/90)^0.8 us minus
+// what hides in the last wave -- and the cheapest wins.  E.g. 321 x 321, B=16: R=10, 10 x 8 tiles, row 320
+// in the tail of the same launch, column 320 as a strip launch on the side lane.  All paths add the 48
+// products of a pixel in the same order, so the result does not depend on the tiling (nor, therefore, on
+// how a batch is sharded).  The model prices the reference's 21 classes; the SM count is the current device's.
 AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
     static const int want[6] = {1, 2, 4, 8, 12, 24};
-    // debugging / A-B aid: PAMR_B200_FORCE_GENERIC=1 routes everything to the generic CUDA kernel
-    static const bool force_generic = []() {
-        const char* e = getenv("PAMR_B200_FORCE_GENERIC");
-        return e != nullptr && e[0] == '1';
-    }();
-    static const int force_rows = getenv("PAMR_B200_ROWS") ? atoi(getenv("PAMR_B200_ROWS")) : 0;
-    static const int strip_max = getenv("PAMR_B200_STRIP_MAX") ? atoi(getenv("PAMR_B200_STRIP_MAX")) : 8;
-    static const int force_strips = getenv("PAMR_B200_FORCE_STRIPS") ? atoi(getenv("PAMR_B200_FORCE_STRIPS")) : 0;
     AffTiling t{0, 0, 0, 0, 0};
-    if (force_generic || dil.nd != 6 || W < TX || H < 8) return t;
+    if (dil.nd != 6 || W < TX || H < 8) return t;
     for (int i = 0; i < 6; ++i)
         if (dil.d[i] != want[i]) return t;
-    const int sms = 148, C = 21;  // the model prices the reference's 21 classes
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || device_sm_count(dev, &sms) != PAMR_OK || sms <= 0) sms = 148;
+    const int C = 21;
     double best_cost = 1e30;
-    for (int r = 8; r <= 10; ++r) {
-        if (force_rows >= 8 && force_rows <= 10 && r != force_rows) continue;
+    for (int r = 8; r <= 10; r += 2) {
         const int ty = NW * r;
-        // R = 9 (odd: scalar tail row, spills at 128 registers) measured ~2x slower per tile: kept for
-        // experiments, effectively never chosen
-        const double tile_us = 2.8 * r * (r == 10 ? 1.00 : r == 9 ? 2.2 : 1.07);
+        const double tile_us = 2.0 * r * (r == 10 ? 1.00 : 1.07);
         const int hrem = H % ty, wrem = W % TX;
-        const bool rs_ok = hrem != 0 && hrem <= strip_max && H > ty;
-        const bool cs_ok = wrem != 0 && wrem <= strip_max && W > TX;
+        const bool rs_ok = hrem != 0 && hrem <= SC_MAX_WC && H > ty;
+        const bool cs_ok = wrem != 0 && wrem <= SC_MAX_WC && W > TX;
         for (int rs = 0; rs < 2; ++rs) {      // rs: row remainder as a strip
-            if (rs ? !rs_ok : (rs_ok && (force_strips & 1))) continue;
+            if (rs && !rs_ok) continue;
             const int ht = rs ? H - hrem : H;
             for (int cs = 0; cs < 2; ++cs) {  // cs: column remainder as a strip launch
-                if (cs ? !cs_ok : (cs_ok && (force_strips & 2))) continue;
+                if (cs && !cs_ok) continue;
                 const int wt = cs ? W - wrem : W;
                 const long long ntiles = (long long)B * ((wt + TX - 1) / TX) * ((ht + ty - 1) / ty);
                 if (ntiles > 0x7fffffffLL) continue;
@@ -943,7 +985,7 @@ AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
                 if (rs) {
                     const long long items = (long long)B * C * hrem * ((W + 31) / 32);
                     const int grid = ntiles < sms ? (int)ntiles : sms;
-                    if (!row_strip_in_tail(items, (int)ntiles, grid)) cost += 8.0 + 1.3e-3 * (double)items;
+                    if (!row_strip_in_tail(items, ntiles, grid)) cost += 8.0 + 1.3e-3 * (double)items;
                 }
                 if (cs) {
                     const double ctas = (double)B * ((H + SC_ROWS - 1) / SC_ROWS);
@@ -961,37 +1003,42 @@ AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
             }
         }
     }
+    if (t.R == 0) return t;  // nothing fits (gigantic B*H*W): the generic kernel takes it
     t.tiles_x = (W + TX - 1) / TX;
     t.tiles_y = (H + NW * t.R - 1) / (NW * t.R);
     return t;
 }
 
-int launch_repack(const float* src, float* dst, int planes, int H, int W, int Wp, cudaStream_t s) {
-    const size_t rows = (size_t)planes * H;
-    const unsigned grid = (unsigned)(rows < 148 * 16 ? rows : 148 * 16);
-    repack_kernel<<<grid, 128, 0, s>>>(src, dst, H, W, Wp, rows);
+// pitch (in 64-bit elements) of the row-pair layout for image width W
+int pair_pitch(int W) { return (W + 1) / 2 * 2; }
+
+int launch_repack_pairs(const float* src, float* dst, int planes, int H, int W, cudaStream_t s) {
+    const int Hp2 = (H + 1) / 2, Wp = pair_pitch(W);
+    const size_t pair_rows = (size_t)planes * Hp2;
+    const unsigned grid = (unsigned)(pair_rows < 148 * 16 ? pair_rows : 148 * 16);
+    repack_pairs_kernel<<<grid, 128, 0, s>>>(src, reinterpret_cast<float2*>(dst), H, W, Hp2, Wp, pair_rows);
     count_launch();
     PAMR_CUDA_TRY(cudaGetLastError());
     return PAMR_OK;
 }
 
-// One propagation step src -> dst: the strip kernels (if the tiling has remainders) followed by the
-// persistent tile kernel.  src must have a pitch that is a multiple of 4 floats and a 16-byte aligned base.
-int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, int src_pitch, float* dst,
-                           int dst_pitch, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s,
+// One propagation step src -> dst: the strip kernels (if the tiling has remainders) and the persistent
+// tile kernel.  src is in the row-pair layout (pitch pair_pitch(W), 16-byte aligned base); dst is in the
+// row-pair layout (dst_pair) or the caller's standard layout.
+int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, float* dst, int dst_pitch,
+                           bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s,
                            SideLane* lane) {
-    static int sm_counts[64] = {0};
-    int sm_count = (dev >= 0 && dev < 64) ? sm_counts[dev] : 0;
-    if (sm_count == 0) {
-        PAMR_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        if (dev >= 0 && dev < 64) sm_counts[dev] = sm_count;
-    }
-    if ((src_pitch & 3) != 0 || ((uintptr_t)src & 15) != 0)
-        return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: source pitch/base not 16-byte aligned");
-    const int Wt = tiling.Wt, Ht = tiling.Ht;
-    if (tiling.R == 8) return launch_one<8>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, lane);
-    if (tiling.R == 9) return launch_one<9>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, lane);
-    return launch_one<10>(aff_tiled, tiling, src, src_pitch, dst, dst_pitch, B, C, H, W, Wt, Ht, cls_max, sm_count, s, lane);
+    int sm_count = 0;
+    int rc = device_sm_count(dev, &sm_count);
+    if (rc != PAMR_OK) return rc;
+    if (((uintptr_t)src & 15) != 0)
+        return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: source base not 16-byte aligned");
+    const int Wt = tiling.Wt, Ht = tiling.Ht, sp = pair_pitch(W);
+    if (tiling.R == 8)
+        return launch_one<8>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, Wt, Ht, cls_max, sm_count, dev, s, lane);
+    if (tiling.R == 10)
+        return launch_one<10>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, Wt, Ht, cls_max, sm_count, dev, s, lane);
+    return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: unsupported tiling R=%d", tiling.R);
 }
 
 }  // namespace pamr

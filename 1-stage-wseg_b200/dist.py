@@ -63,7 +63,11 @@ class ShardedPseudoLabeler:
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         B = image_raw.shape[0]
         lo, hi = shard_range(B, rank, world)
-        local = refine_and_label(self.pamr, image_raw[lo:hi], masks[lo:hi], labels[lo:hi], out_size)
+        if hi > lo:
+            local = refine_and_label(self.pamr, image_raw[lo:hi], masks[lo:hi], labels[lo:hi], out_size)
+        else:  # B < world: this rank's shard is empty; it still takes part in the gather (the C API rejects B < 1)
+            H, W = (int(out_size[0]), int(out_size[1])) if out_size is not None else tuple(image_raw.shape[-2:])
+            local = torch.empty((0, H, W), dtype=torch.uint8, device=image_raw.device)
         if not gather or world == 1:
             return local
         return gather_labels(local, B, self.group)

@@ -121,10 +121,17 @@ def pseudo_gtmask(mask, cutoff_top=0.6, cutoff_low=0.2, eps=1e-8):
 
 
 def labels_from_pseudo_gt(pseudo_gt, ignore_index=IGNORE_INDEX):
-    """argmax + ignore (SoftMaxAE.py:61-67) for callers that hold a float pseudo_gt already."""
-    mask_gt = torch.argmax(pseudo_gt, 1)
-    mask_gt[pseudo_gt.sum(1) < 1.] = ignore_index
-    return mask_gt
+    """argmax + ignore (SoftMaxAE.py:61-67) for callers that hold a float pseudo_gt already: int64 label
+    map like the reference's (one kernel, pamr_labels_from_onehot_f32; the uint8 map widened on the device)."""
+    pg = _check_cuda_f32("pseudo_gt", pseudo_gt)
+    B, C, H, W = pg.shape
+    lab = torch.empty((B, H, W), dtype=torch.uint8, device=pg.device)
+    _lib.check(_lib.lib().pamr_labels_from_onehot_f32(pg.data_ptr(), lab.data_ptr(), None, B, C, H, W, _dev(pg),
+                                                      _stream(pg.device)))
+    out = lab.long()
+    if ignore_index != IGNORE_INDEX:
+        out[lab == IGNORE_INDEX] = ignore_index
+    return out
 
 
 def refine_and_label(pamr, image_raw, masks, labels, out_size=None, return_masks=False, return_counts=False, denorm=None):

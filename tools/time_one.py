@@ -19,7 +19,11 @@ def t(fn, n=10):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
+pamr2 = wseg_b200.PAMR(20, D6).to(dev)
 fw = t(lambda: pamr(image, mask))
+fw2 = t(lambda: pamr2(image, mask))
+print("H=%d W=%d B=%d  marginal launch %.4f ms = %.1f%% of the HBM roofline (360 B/px at 6543.1 GB/s); forward(10) %.3f ms" % (
+    H, W, B, (fw2 - fw) / 10, 100 * 360e-9 * B * H * W / ((fw2 - fw) / 10 * 1e-3) / 6543.1, fw), flush=True)
 af = t(lambda: wseg_b200.local_affinity(image, D6))
 print("H=%d W=%d B=%d  forward %.3f ms (affinity-std alone %.3f ms) -> (fwd-aff)/10 = %.3f ms/iter ; tags %s %s" % (
     H, W, B, fw, af, (fw - af) / 10, os.environ.get("PAMR_B200_STAGGER_CTA", "-"), os.environ.get("PAMR_B200_STAGGER_GRP", "-")), flush=True)

@@ -1,4 +1,5 @@
-"""Print the per-pass timeline of CTA 0 of one tuned propagation launch (debug hook)."""
+"""Print the per-pass timeline of one CTA of one tuned propagation launch (experiment builds only:
+tools/build_variant.sh NAME pamr_propagate_sm100.cu -DPAMR_EXPERIMENTS, then PAMR_LIB=... python tools/timeline.py)."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -6,50 +7,57 @@ import torch, wseg_b200
 D6 = [1, 2, 4, 8, 12, 24]
 dev = "cuda:0"
 B, C, H, W = 16, 21, int(os.environ.get("PROF_H", 320)), int(os.environ.get("PROF_W", 320))
+CTA = int(os.environ.get("PROF_CTA", 0))
 image = torch.rand((B, 3, H, W), device=dev); mask = torch.softmax(2 * torch.randn((B, C, H, W), device=dev), 1)
 aff = wseg_b200.local_affinity(image, D6)
-for _ in range(3): wseg_b200.propagate(aff, mask, D6, 1)
-buf = torch.zeros((3, 4096, 2), dtype=torch.int64, device=dev)
+for _ in range(3): wseg_b200.propagate(aff, mask, D6, 2)
+buf = torch.zeros((5, 4096, 2), dtype=torch.int64, device=dev)
 raw = ctypes.CDLL(wseg_b200._lib.LIB_PATH)
-raw.pamr_debug_set_timeline.argtypes = [ctypes.c_void_p]
+raw.pamr_debug_set_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
 torch.cuda.synchronize()
-raw.pamr_debug_set_timeline(buf.data_ptr())
-wseg_b200.propagate(aff, mask, D6, 1)
+raw.pamr_debug_set_timeline(buf.data_ptr(), CTA, 1)   # record the 2nd of 3 iterations (row-pair in, row-pair out)
+wseg_b200.propagate(aff, mask, D6, 3)
 torch.cuda.synchronize()
-raw.pamr_debug_set_timeline(None)
 ev = buf.cpu().numpy()
-t0 = min(ev[g, 0, 0] for g in range(2))
-issue = {int(c) - 1000: int(t) for t, c in ev[2] if c >= 1000}
-names = {5: "tma-landed", 1: "tile-begin", 2: "bar1-done", 3: "fill-done", 4: "bar2-done", 6: "wait-done", 7: "syncwarp-done", 9: "acc-ready", 8: "store-done"}
-for g in range(2):
+t0 = min(int(ev[g, 0, 0]) for g in range(3) if ev[g, 0, 0] > 0)
+issue = {}
+names = {6: "wait-done", 9: "acc-ready", 8: "store-done"}
+TILES = [int(x) for x in os.environ.get("PROF_TILES", "3,4").split(",")]
+for g in range(3):
     print("---- group", g)
-    prev = None; ntile = 0
+    prev = None; ntile = 0; lastk = 99
     for t, code in ev[g]:
         if t == 0: break
-        if code == 1: ntile += 1
-        if ntile in (3, 4):
-            nm = names.get(int(code), "pass %d begin" % (code - 100))
+        t, code = int(t), int(code)
+        if code >= 100:
+            k = code - 100
+            if k < lastk: ntile += 1
+            lastk = k
+        if ntile in TILES:
+            nm = names.get(code, "pass %d begin" % (code - 100))
             if code >= 100:
-                n = (ntile - 1) * C + int(code - 100)
-                nm += "   (TMA for this class issued at %d = %d cycles earlier)" % (issue.get(n, 0) - t0, t - issue.get(n, 0))
+                nn = (ntile - 1) * C + (code - 100)
+                if nn in issue: nm += "   (TMA issued %d cycles earlier)" % (t - issue[nn])
             print("%10d  +%7d  %s" % (t - t0, 0 if prev is None else t - prev, nm))
         prev = t
-
-# per-tile summary for group 0: fill, blocking waits, compute
-import collections
-g = 0
-rows = [(int(t), int(c)) for t, c in ev[g] if t != 0]
-tiles = []
-cur = None
-for i, (t, c) in enumerate(rows):
-    if c == 1:
-        cur = {"begin": t, "wait": 0, "fill": 0, "n": 0}
-        tiles.append(cur)
-    elif c == 2: cur["b1"] = t
-    elif c == 3: cur["fill"] = t - cur["b1"]
-    elif c >= 100: cur["pb"] = t
-    elif c == 6: cur["wait"] += t - cur["pb"]; cur["n"] += 1
-    elif c == 8: cur["end"] = t
-print("tile summaries (group 0): total / fill / sum of waits")
-for tl in tiles[:10]:
-    if "end" in tl: print("  total %7d  fill %6d  waits %6d over %d passes" % (tl["end"] - tl["begin"], tl["fill"], tl["wait"], tl["n"]))
+for st, nm in ((3, "loader (2000+u: bulk copy of unit u issued)"), (4, "issuer (2100+u: unit u staged and free, tcgen05.cp issued)")):
+    print("----", nm)
+    prev = None; ntile = 0; lastu = 99
+    for t, code in ev[st]:
+        if t == 0: break
+        t, code = int(t), int(code)
+        u = code % 100
+        if u < lastu: ntile += 1
+        lastu = u
+        if ntile in TILES or ntile - 1 in TILES:
+            print("%10d  +%7d  tile %d  %d" % (t - t0, 0 if prev is None else t - prev, ntile, code))
+        prev = t
+# per-tile summary per group
+for g in range(3):
+    rows = [(int(t), int(c)) for t, c in ev[g] if t != 0]
+    starts = []; lastk = 99
+    for t, c in rows:
+        if c >= 100:
+            if c - 100 < lastk: starts.append(t)
+            lastk = c - 100
+    print("group %d tile durations:" % g, [b - a for a, b in zip(starts, starts[1:])][:12])

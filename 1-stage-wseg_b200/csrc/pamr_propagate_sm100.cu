@@ -65,12 +65,12 @@ static_assert(NBAR % NSLOT == 0 && NBAR >= 2 * NSLOT, "barrier ring must cover a
 // ring), 14 and 15 weight issuers (tcgen05.cp staging -> TMEM; even / odd units).
 constexpr int W_PRODUCER = NWC, W_LOADER = NWC + 1, W_ISSUER = NWC + 2;
 constexpr int NTHREADS = (NWC + 4) * 32;
-constexpr int NSTG = 6;               // staging ring for the weights: NSTG units of 16 KB ...
-constexpr int NPAIR = NSTG / 2;       // ... managed as pair-stages of two consecutive units
+constexpr int CHUNK_UNITS = 2;        // units handed over together ("chunk": 64 TMEM columns, 32 KB; the last chunk of a tile may be short)
+constexpr int NSTG = 3;               // staging ring for the weights: NSTG chunks of 32 KB
 constexpr int WB = 16;                // weights per tcgen05.ld batch of the centre column
 constexpr int UNIT = 32;              // TMEM columns per fill unit (= 2 batches)
 constexpr int UNIT_BYTES = UNIT * 128 * 4;  // 128 TMEM lanes
-constexpr int MAX_UNITS = 16;
+constexpr int MAX_CHUNKS = 8;
 constexpr int CTRL_BYTES = 1024;
 
 __host__ __device__ constexpr int dil_of(int id) { return id == 0 ? 1 : id == 1 ? 2 : id == 2 ? 4 : id == 3 ? 8 : id == 4 ? 12 : 24; }
@@ -169,7 +169,7 @@ struct Cfg {
     static constexpr int SLOT_FLOATS = WIN_W * WIN_H;
     static constexpr int SLOT_BYTES = SLOT_FLOATS * 4;
     static constexpr size_t STAGE_OFF = (size_t)NSLOT * SLOT_BYTES;             // weight staging ring (1024-byte aligned)
-    static constexpr size_t CTRL_OFF = STAGE_OFF + (size_t)NSTG * UNIT_BYTES;
+    static constexpr size_t CTRL_OFF = STAGE_OFF + (size_t)NSTG * CHUNK_UNITS * UNIT_BYTES;
     static constexpr size_t SMEM_BYTES = CTRL_OFF + CTRL_BYTES;
     static_assert(SLOT_BYTES % 128 == 0 && STAGE_OFF % 128 == 0, "TMA / bulk destinations");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
@@ -178,10 +178,10 @@ struct Cfg {
 struct Ctrl {  // lives in the last CTRL_BYTES of dynamic shared memory
     unsigned long long tma_bar[NBAR];           // class plane landed in its slot
     unsigned long long empty_bar[NBAR];         // class plane consumed
-    unsigned long long filled_bar[MAX_UNITS];   // the tile's weights of that unit are in TMEM (tcgen05.commit)
-    unsigned long long free_bar[MAX_UNITS];     // every compute warp has read the unit for the last time in this tile
-    unsigned long long staged_bar[NPAIR];       // the pair's 2 x 16 KB have landed in the staging ring
-    unsigned long long stage_free_bar[NPAIR];   // both units of the pair have been copied on to TMEM
+    unsigned long long filled_bar[MAX_CHUNKS];  // the tile's weights of that chunk are in TMEM (tcgen05.commit)
+    unsigned long long free_bar[MAX_CHUNKS];    // every compute warp has read the chunk for the last time in this tile
+    unsigned long long staged_bar[2 * NSTG];    // the chunk's bytes have landed in the staging ring (chunk n: stage n % NSTG,
+                                                // barrier n % (2 NSTG), so that a barrier's consecutive phases belong to ONE issuer)
     uint32_t tmem_base;
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block");
@@ -243,8 +243,10 @@ struct TmemLayout {
     static constexpr int NCOLS = 48 * R;          // 480 (R = 10) or 384 (R = 8) of the 512 columns
     static constexpr int NB = NCOLS / WB;         // batches per pass
     static constexpr int NU = NCOLS / UNIT;       // fill units per tile
+    static constexpr int NCH = (NU + CHUNK_UNITS - 1) / CHUNK_UNITS;  // chunks per tile
+    static constexpr int BPC = CHUNK_UNITS * UNIT / WB;               // batches per (full) chunk
     static_assert(NCOLS % UNIT == 0 && NCOLS <= 512, "TMEM columns");
-    static_assert(NU <= MAX_UNITS, "fill units");
+    static_assert(NCH <= MAX_CHUNKS, "chunks");
 };
 
 // ---------------------------------------------------------------- compute body
@@ -285,17 +287,18 @@ __device__ __forceinline__ void compute_pass(const float* __restrict__ sp, uint3
                                              uint32_t filled_bar, uint32_t free_bar, uint32_t par, int lane) {
     using L = TmemLayout<R>;
     // The weights stream through two 16-register buffers in consumption order: batch b (TMEM columns
-    // [16b, 16b+16)) lives in wb[b & 1] and belongs to fill unit b / 2.  All indices are compile-time.
+    // [16b, 16b+16)) lives in wb[b & 1] and belongs to chunk b / BPC.  All indices are compile-time.
     float wb[2][WB];
-    // entering batch b (its load was issued one batch earlier): wait for it, release its unit if this was
-    // the unit's second batch, and issue the load of batch b + 1
+    // entering batch b (its load was issued one batch earlier): wait for it, release its chunk if this was
+    // the chunk's last batch, and issue the load of batch b + 1 (first pass of a tile: once its chunk is filled)
 #define PAMR_ENTER_BATCH(b)                                                                      \
     do {                                                                                         \
         tmem_wait_ld(wb[(b) & 1]);                                                               \
-        if (free_bar && ((b) & 1)) signal_free(free_bar + 8 * ((b) >> 1), lane);                 \
+        if (free_bar && (((b) % L::BPC) == L::BPC - 1 || (b) == L::NB - 1))                      \
+            signal_free(free_bar + 8 * ((b) / L::BPC), lane);                                    \
         if ((b) + 1 < L::NB) {                                                                   \
-            if (filled_bar && (((b) + 1) & 1) == 0) {                                            \
-                mbar_wait(filled_bar + 8 * (((b) + 1) >> 1), par);                               \
+            if (filled_bar && (((b) + 1) % L::BPC) == 0) {                                       \
+                mbar_wait(filled_bar + 8 * (((b) + 1) / L::BPC), par);                           \
                 tc_fence_after();                                                                \
             }                                                                                    \
             tmem_ld16(tbase + ((b) + 1) * WB, wb[((b) + 1) & 1]);                                \
@@ -487,14 +490,11 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             mbar_init(smem_u32(&ctrl->tma_bar[s]), 1);
             mbar_init(smem_u32(&ctrl->empty_bar[s]), NW);  // the NW warps of the group that read the slot
         }
-        for (int u = 0; u < MAX_UNITS; ++u) {
-            mbar_init(smem_u32(&ctrl->filled_bar[u]), 1);                  // tcgen05.commit of the issuer
+        for (int u = 0; u < MAX_CHUNKS; ++u) {
+            mbar_init(smem_u32(&ctrl->filled_bar[u]), 1);                  // tcgen05.commit of an issuer
             mbar_init(smem_u32(&ctrl->free_bar[u]), NW * active_groups);   // every compute warp that reads weights
         }
-        for (int g = 0; g < NPAIR; ++g) {
-            mbar_init(smem_u32(&ctrl->staged_bar[g]), 1);
-            mbar_init(smem_u32(&ctrl->stage_free_bar[g]), 2);  // one tcgen05.commit per issuer
-        }
+        for (int g = 0; g < 2 * NSTG; ++g) mbar_init(smem_u32(&ctrl->staged_bar[g]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -553,52 +553,51 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         }
     } else if (warp == W_LOADER) {
         // ===================== weight loader: L2 -> staging ring with cp.async.bulk =====================
-        // The tiles' units form one stream n = tile_iter * NU + unit.  Two consecutive units share a
-        // pair-stage p = (n / 2) % NPAIR of the ring and one `staged` barrier (a control thread on a saturated SM
-        // pays a few hundred cycles per mbarrier round trip, so the loop is kept to one wait per 32 KB).  A
-        // pair-stage is reusable once both tcgen05.cp sets that read it have completed: each issuer commits
-        // onto `stage_free` after its unit.
+        // The tiles' chunks form one stream n = tile_iter * NCH + chunk; chunk n uses stage n % NSTG.  A stage is
+        // reusable once the tcgen05.cp set that read it has completed, which is what filled_bar of that chunk
+        // reports.  (A control thread on a saturated SM pays a few hundred cycles per mbarrier round trip, hence
+        // 32 KB per loop iteration.)
         if (lane == 0) {
-            const int total = my_tiles * L::NU;
+            const int total = my_tiles * L::NCH;
             [[maybe_unused]] int ev_n = 0;
-            for (int n0 = 0; n0 < total; n0 += 2) {
-                const int m = n0 >> 1, p = m % NPAIR;
-                if (m >= NPAIR) mbar_wait(smem_u32(&ctrl->stage_free_bar[p]), (uint32_t)(m / NPAIR - 1) & 1u);
-                const int cnt = (n0 + 1 < total) ? 2 : 1;
-                const uint32_t bar = smem_u32(&ctrl->staged_bar[p]);
-                mbar_arrive_expect_tx(bar, cnt * UNIT_BYTES);
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (j < cnt) {
-                        const int n = n0 + j, ti = n / L::NU, u = n % L::NU;
-                        bulk_load(smem_u32(stage_ring + (size_t)(2 * p + j) * UNIT_BYTES), tile_weights(ti) + (size_t)u * (UNIT * 128),
-                                  UNIT_BYTES, bar);
-                    }
+            for (int n = 0; n < total; ++n) {
+                const int ti = n / L::NCH, c = n % L::NCH, g = n % NSTG;
+                if (n >= NSTG) {
+                    const int pn = n - NSTG;
+                    mbar_wait(smem_u32(&ctrl->filled_bar[pn % L::NCH]), (uint32_t)(pn / L::NCH) & 1u);
                 }
-                PAMR_EV(3, true, 2000 + (n0 % L::NU));
+                const int units = min(CHUNK_UNITS, L::NU - c * CHUNK_UNITS);
+                const uint32_t bar = smem_u32(&ctrl->staged_bar[n % (2 * NSTG)]);
+                mbar_arrive_expect_tx(bar, units * UNIT_BYTES);
+                bulk_load(smem_u32(stage_ring + (size_t)g * (CHUNK_UNITS * UNIT_BYTES)),
+                          tile_weights(ti) + (size_t)c * (CHUNK_UNITS * UNIT * 128), units * UNIT_BYTES, bar);
+                PAMR_EV(3, true, 2000 + c);
             }
         }
     } else if (warp >= W_ISSUER) {
         // ===================== weight issuers: staging ring -> TMEM with tcgen05.cp =====================
-        // two control threads (warps 14 and 15), even and odd units of the stream
+        // two control threads (warps 14 and 15) take the even and the odd chunks of the stream
         if (lane == 0) {
-            const int total = my_tiles * L::NU;
+            const int total = my_tiles * L::NCH;
             const uint32_t tb = ctrl->tmem_base;
             [[maybe_unused]] int ev_n = 0;
-            for (int n = warp - W_ISSUER; n < total; n += 2) {
-                const int ti = n / L::NU, u = n % L::NU, m = n >> 1, p = m % NPAIR;
-                mbar_wait(smem_u32(&ctrl->staged_bar[p]), (uint32_t)(m / NPAIR) & 1u);  // bytes landed
-                if (ti > 0) mbar_wait(smem_u32(&ctrl->free_bar[u]), (uint32_t)(ti - 1) & 1u);  // the previous tile's last passes have read the unit
+            int n = warp - W_ISSUER;
+            static_assert(L::NCH % 2 == 0, "a chunk index must always meet the same issuer (mbarrier waits are by phase parity)");
+            if (n < total) mbar_wait(smem_u32(&ctrl->staged_bar[n % (2 * NSTG)]), (uint32_t)(n / (2 * NSTG)) & 1u);  // bytes landed
+            for (; n < total; n += 2) {
+                const int ti = n / L::NCH, c = n % L::NCH, g = n % NSTG;
+                if (ti > 0) mbar_wait(smem_u32(&ctrl->free_bar[c]), (uint32_t)(ti - 1) & 1u);  // the previous tile's last passes have read the chunk
                 tc_fence_after();
-                PAMR_EV(4, warp == W_ISSUER, 2100 + u);
-                const uint32_t sa = smem_u32(stage_ring + (size_t)(2 * p + (n & 1)) * UNIT_BYTES);
+                PAMR_EV(4, warp == W_ISSUER, 2100 + c);
+                const int units = min(CHUNK_UNITS, L::NU - c * CHUNK_UNITS);
+                const uint32_t sa = smem_u32(stage_ring + (size_t)g * (CHUNK_UNITS * UNIT_BYTES));
 #pragma unroll
-                for (int k = 0; k < UNIT / 8; ++k)  // 8 columns each: pieces 2k, 2k+1 (2 KB apart), 8-lane groups 128 B apart
-                    utccp_128x256b(tb + u * UNIT + k * 8, utccp_desc(sa + k * 4096, 2048, 128));
-                utccp_commit(smem_u32(&ctrl->filled_bar[u]));
-                utccp_commit(smem_u32(&ctrl->stage_free_bar[p]));
+                for (int k = 0; k < CHUNK_UNITS * UNIT / 8; ++k)  // 8 columns each: pieces 2k, 2k+1 (2 KB apart), 8-lane groups 128 B apart
+                    if (k < units * (UNIT / 8)) utccp_128x256b(tb + c * (CHUNK_UNITS * UNIT) + k * 8, utccp_desc(sa + k * 4096, 2048, 128));
+                utccp_commit(smem_u32(&ctrl->filled_bar[c]));
+                // while the next chunk is still being read: make sure its bytes have landed
+                if (n + 2 < total) mbar_wait(smem_u32(&ctrl->staged_bar[(n + 2) % (2 * NSTG)]), (uint32_t)((n + 2) / (2 * NSTG)) & 1u);
             }
-            // a lone last unit has no partner: its pair-stage is never reused, nothing to balance
         }
     } else if (warp < NWC) {
         // ===================== compute warps: NG groups x NW warps =====================

@@ -50,10 +50,11 @@ affinity_kernel(const float* __restrict__ img, float* __restrict__ aff, int K, i
         if (TILED) {
             // inside a partial tile but outside the image: the propagation kernel expects zeros
             if (x < tiling.tiles_x * 32 && y < tiling.tiles_y * 4 * tiling.R) {
-                int ti = 0;
-                float* __restrict__ out = aff + aff_tiled_pixel_base(tiling, b, y, x, &ti);
+                AffTiling full = tiling;  // address it as a tile pixel (it is neither of the strips)
+                full.Wt = tiling.tiles_x * 32; full.Ht = tiling.tiles_y * 4 * tiling.R;
+                const AffPixel px = aff_pixel(full, b, y, x);
 #pragma unroll
-                for (int s = 0; s < 48; ++s) out[aff_tiled_col_offset(s * tiling.R + ti)] = 0.f;
+                for (int s = 0; s < 48; ++s) aff[px.at(s)] = 0.f;
             }
         }
         return;
@@ -130,10 +131,9 @@ affinity_kernel(const float* __restrict__ img, float* __restrict__ aff, int K, i
     }
     const float rs = __frcp_rn(s);  // s in [1, P]
     if (TILED) {
-        int ti = 0;
-        float* __restrict__ out = aff + aff_tiled_pixel_base(tiling, b, y, x, &ti);
+        const AffPixel px = aff_pixel(tiling, b, y, x);
 #pragma unroll
-        for (int p = 0; p < 8 * MAXND; ++p) out[aff_tiled_col_offset(tap_seq(p) * tiling.R + ti)] = div_markstein(abar[p], s, rs);
+        for (int p = 0; p < 8 * MAXND; ++p) aff[px.at(tap_seq(p))] = div_markstein(abar[p], s, rs);
     } else {
         float* __restrict__ out = aff + (size_t)b * P * HW + (size_t)y * W + x;
 #pragma unroll
@@ -188,10 +188,11 @@ affinity_smem_kernel(const float* __restrict__ img, float* __restrict__ aff, int
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= W || y >= H) {
         if (TILED && x < tiling.tiles_x * 32 && y < tiling.tiles_y * 4 * tiling.R) {
-            int ti = 0;
-            float* __restrict__ out = aff + aff_tiled_pixel_base(tiling, b, y, x, &ti);
+            AffTiling full = tiling;  // a partial tile's pixel outside the image: zeros
+            full.Wt = tiling.tiles_x * 32; full.Ht = tiling.tiles_y * 4 * tiling.R;
+            const AffPixel px = aff_pixel(full, b, y, x);
 #pragma unroll
-            for (int s = 0; s < 48; ++s) out[aff_tiled_col_offset(s * tiling.R + ti)] = 0.f;
+            for (int s = 0; s < 48; ++s) aff[px.at(s)] = 0.f;
         }
         return;
     }
@@ -261,10 +262,9 @@ affinity_smem_kernel(const float* __restrict__ img, float* __restrict__ aff, int
     }
     const float rs = __frcp_rn(s);
     if (TILED) {
-        int ti = 0;
-        float* __restrict__ out = aff + aff_tiled_pixel_base(tiling, b, y, x, &ti);
+        const AffPixel px = aff_pixel(tiling, b, y, x);
 #pragma unroll
-        for (int p = 0; p < 48; ++p) out[aff_tiled_col_offset(tap_seq(p) * tiling.R + ti)] = div_markstein(abar[p], s, rs);
+        for (int p = 0; p < 48; ++p) aff[px.at(tap_seq(p))] = div_markstein(abar[p], s, rs);
     } else {
         float* __restrict__ out = aff + (size_t)b * 48 * HW + (size_t)y * W + x;
 #pragma unroll
@@ -285,14 +285,15 @@ aff_relayout_kernel(const float* __restrict__ src, float* __restrict__ dst, int 
     const int x = blockIdx.x * AFF_BX + threadIdx.x;
     const int y = blockIdx.y * AFF_BY + threadIdx.y;
     const int b = blockIdx.z;
-    if (x >= tiling.tiles_x * 32 || y >= tiling.tiles_y * 4 * tiling.R) return;
     const bool in = (x < W) && (y < H);
+    if (!in && (x >= tiling.tiles_x * 32 || y >= tiling.tiles_y * 4 * tiling.R)) return;
     const size_t HW = (size_t)H * W;
     const float* __restrict__ ip = src + (size_t)b * 48 * HW + (size_t)y * W + x;
-    int ti = 0;
-    float* __restrict__ out = dst + aff_tiled_pixel_base(tiling, b, y, x, &ti);
+    AffTiling full = tiling;
+    if (!in) { full.Wt = tiling.tiles_x * 32; full.Ht = tiling.tiles_y * 4 * tiling.R; }  // partial-tile padding: zeros
+    const AffPixel px = aff_pixel(full, b, y, x);
 #pragma unroll 8
-    for (int p = 0; p < 48; ++p) out[aff_tiled_col_offset(tap_seq(p) * tiling.R + ti)] = in ? __ldg(ip + (size_t)p * HW) : 0.f;
+    for (int p = 0; p < 48; ++p) dst[px.at(tap_seq(p))] = in ? __ldg(ip + (size_t)p * HW) : 0.f;
 }
 
 }  // namespace
@@ -300,7 +301,7 @@ aff_relayout_kernel(const float* __restrict__ src, float* __restrict__ dst, int 
 int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, const Dilations& dil,
                     const AffTiling& tiling, cudaStream_t s) {
     const bool tiled = tiling.R > 0;
-    const int gw = tiled ? tiling.tiles_x * 32 : W, gh = tiled ? tiling.tiles_y * 4 * tiling.R : H;
+    const int gw = tiled ? max(tiling.tiles_x * 32, W) : W, gh = tiled ? max(tiling.tiles_y * 4 * tiling.R, H) : H;
     if (standard_dilations(dil) && K <= SA_MAXK) {
         dim3 sblock(SA_BX, SA_BY);
         dim3 sgrid((gw + SA_BX - 1) / SA_BX, (gh + SA_BY - 1) / SA_BY, B);
@@ -343,7 +344,8 @@ int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, co
 int launch_aff_relayout(const float* aff_std, float* aff_tiled, int B, int H, int W, const AffTiling& tiling,
                         cudaStream_t s) {
     dim3 block(AFF_BX, AFF_BY);
-    dim3 grid(tiling.tiles_x, (tiling.tiles_y * 4 * tiling.R + AFF_BY - 1) / AFF_BY, B);
+    const int gw = max(tiling.tiles_x * 32, W), gh = max(tiling.tiles_y * 4 * tiling.R, H);
+    dim3 grid((gw + AFF_BX - 1) / AFF_BX, (gh + AFF_BY - 1) / AFF_BY, B);
     if (grid.y > 65535 || grid.z > 65535)
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "affinity relayout: H/4 and B must be <= 65535");
     aff_relayout_kernel<<<grid, block, 0, s>>>(aff_std, aff_tiled, H, W, tiling);

@@ -143,7 +143,7 @@ int pamr_affinity_f32(const float* img, float* aff, int B, int K, int H, int W, 
     PAMR_TRY(check_dims(B, K, H, W));
     Dilations dil;
     PAMR_TRY(make_dilations(dilations, nd, &dil));
-    return launch_affinity(img, aff, B, K, H, W, dil, AffTiling{0, 0, 0, 0, 0}, (cudaStream_t)stream);
+    return launch_affinity(img, aff, B, K, H, W, dil, AffTiling{}, (cudaStream_t)stream);
 }
 
 size_t pamr_propagate_scratch_bytes(int B, int C, int H, int W, const int* dilations, int nd, int iters) {
@@ -176,7 +176,7 @@ ForwardPlan plan_forward(int B, int C, int H, int W, int h, int w, const Dilatio
     ForwardPlan p;
     const size_t HW = (size_t)H * W;
     p.tiling = tuned_tiling(B, H, W, dil);
-    const size_t aff_floats = p.tiling.R > 0 ? aff_tiled_floats(B, p.tiling) : (size_t)B * 8 * dil.nd * HW;
+    const size_t aff_floats = p.tiling.R > 0 ? p.tiling.floats : (size_t)B * 8 * dil.nd * HW;
     p.aff_bytes = align_up(sizeof(float) * aff_floats, 256);
     p.scratch_bytes = align_up(propagate_scratch_bytes(B, C, H, W, dil, iters, p.tiling.R > 0), 256);
     p.resize_bytes = (h != H || w != W) ? align_up(sizeof(float) * (size_t)B * C * HW, 256) : 0;
@@ -320,7 +320,7 @@ int pamr_pseudo_labels_host_f32(const float* h_img, const float* h_mask, const f
     const size_t n_img = sizeof(float) * (size_t)B * K * HW, n_ims = sizeof(float) * (size_t)B * K * hw;
     const size_t n_mask = sizeof(float) * (size_t)B * C * hw, n_lab = sizeof(float) * (size_t)B * (C - 1);
     const AffTiling tiling = tuned_tiling(B, h, w, dil);
-    const size_t n_aff = sizeof(float) * (tiling.R > 0 ? aff_tiled_floats(B, tiling) : (size_t)B * 8 * nd * hw);
+    const size_t n_aff = sizeof(float) * (tiling.R > 0 ? tiling.floats : (size_t)B * 8 * nd * hw);
     const size_t n_out = (size_t)B * HW;
     const size_t n_max = sizeof(unsigned) * (size_t)B * C;
     const bool resize = (h != H || w != W);

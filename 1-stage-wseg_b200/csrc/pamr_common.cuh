@@ -23,15 +23,23 @@ __device__ __forceinline__ int tap_dx(int j) {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
-// ---- tile-major affinity layout consumed by the tuned sm_100a propagation kernel ----
-// Only for the standard 6 dilations (48 taps).  The tuned kernel's thread (lane quarter wq, lane) of tile
-// (ty,tx) owns R pixels (rows ty*4R + wq*R + i, column tx*32 + lane) and keeps their 48*R weights in its
-// Tensor Memory lane l = wq*32 + lane, at column s*R + i ("sequence" order s below).  The weights travel
-// global -> shared memory (cp.async.bulk) -> TMEM (tcgen05.cp) without passing through registers, so the
-// global layout IS the shared-memory image tcgen05.cp reads: 16-byte pieces of 4 consecutive columns per lane,
-//   [b][ty][tx][column / 4][l = 0..127][column % 4]
-// (128 lanes x 16 bytes = 2 KB per piece; 8 pieces = one 16 KB fill unit of 32 columns).
-// Pixels of partial tiles that lie outside the image hold zeros.
+// ---- affinity layout consumed by the tuned sm_100a propagation kernel ----
+// Only for the standard 6 dilations (48 taps).  Three regions (AffTiling holds their bases):
+//  * tiles, covering [0,Wt) x [0,Ht) (rounded up to whole tiles when a remainder is not split off): the tuned
+//    kernel's thread (lane quarter wq, lane) of tile (ty,tx) owns R pixels (rows ty*4R + wq*R + i, column
+//    tx*32 + lane) and keeps their 48*R weights in its Tensor Memory lane l = wq*32 + lane, at column s*R + i
+//    ("sequence" order s below).  The weights travel global -> shared memory (cp.async.bulk) -> TMEM
+//    (tcgen05.cp) without passing through registers, so the global layout IS the shared-memory image
+//    tcgen05.cp reads: 16-byte pieces of 4 consecutive columns per lane,
+//        [b][ty][tx][column / 4][l = 0..127][column % 4]
+//    (128 lanes x 16 bytes = 2 KB per piece; 8 pieces = one 16 KB fill unit of 32 columns).  Pixels of partial
+//    tiles that lie outside the image hold zeros;
+//  * the column strip x = Wt = W-1 (one column, e.g. W = 321), y < Ht: the tiles on the right image border compute
+//    it from their own shared-memory window.  LP = 32/R lanes share a strip pixel (48/LP taps each), and the
+//    weights sit in spare Tensor Memory columns of those lanes, so this region is a tcgen05.cp image as well: per
+//    (b, ty) a block of [k / 4][l = 0..127][k % 4] with k < 48/LP the lane's tap and l = wq*32 + i*LP + part the
+//    lane that owns taps [part*48/LP, (part+1)*48/LP) of strip pixel (row wq*R + i of the tile);
+//  * the row strip y in [Ht,H) (at most 8 rows), all x:  [b][y - Ht][s][x]  (coalesced for one warp per 32 pixels).
 //
 // Tap sequence s (0..47) <-> reference tap p = 8*id + j (pamr.py:25-34):
 //   s <  12: centre column (b = 0): id = s/2, j = 1 (dy=-d) or 6 (dy=+d)
@@ -52,26 +60,60 @@ __host__ __device__ constexpr int tap_seq(int p) {
 }
 struct AffTiling {
     int R, tiles_x, tiles_y;  // R rows per thread (tile = 32 x 4R); R == 0: standard [B,48,H,W] layout
-    int Wt, Ht;               // host-side: extent covered by tiles (the rest goes to the strip kernels)
+    int Wt, Ht;               // extent covered by tiles; x >= Wt is the column strip, y >= Ht the row strip
+    int W, H;
+    size_t cs_base, rs_base;  // float offsets of the column-strip and row-strip regions
+    size_t floats;            // total size of the layout
 };
-__host__ __device__ __forceinline__ size_t aff_tiled_floats(int B, const AffTiling& t) {
-    return (size_t)B * t.tiles_y * t.tiles_x * 48 * t.R * 128;
-}
-// offset of weight (s, i) relative to the pixel's base (aff_tiled_index with s = 0 at a pixel with i = 0 ... see below)
+// offset of TMEM column `col` of a lane relative to the lane's first weight
 __host__ __device__ __forceinline__ size_t aff_tiled_col_offset(int col) { return ((size_t)(col >> 2) << 9) + (size_t)(col & 3); }
-// index of weight s of pixel (y, x)
-__host__ __device__ __forceinline__ size_t aff_tiled_index(const AffTiling& t, int b, int s, int y, int x) {
-    const int ty = y / (4 * t.R), ry = y % (4 * t.R), wq = ry / t.R, i = ry % t.R;
-    const size_t tile = ((size_t)b * t.tiles_y + ty) * t.tiles_x + (x >> 5);
-    return tile * ((size_t)48 * t.R * 128) + (size_t)(wq * 32 + (x & 31)) * 4 + aff_tiled_col_offset(s * t.R + i);
+__host__ __device__ __forceinline__ size_t aff_tile_floats(int R) { return (size_t)48 * R * 128; }
+// column strip: lanes per strip pixel, taps per lane, floats of one (b, ty) block
+__host__ __device__ constexpr int aff_cs_lanes(int R) { return 32 / R; }
+__host__ __device__ constexpr int aff_cs_taps(int R) { return 48 / (32 / R); }
+__host__ __device__ constexpr size_t aff_cs_block_floats(int R) { return (size_t)aff_cs_taps(R) * 128; }
+// fills the derived fields (region bases, size) for a batch of B
+__host__ __device__ __forceinline__ void aff_layout_finish(AffTiling& t, int B) {
+    const size_t tiled = (size_t)B * t.tiles_y * t.tiles_x * aff_tile_floats(t.R);
+    const size_t cs = (t.W > t.Wt) ? (size_t)B * t.tiles_y * aff_cs_block_floats(t.R) : 0;
+    const size_t rs = (size_t)B * (t.H - t.Ht) * 48 * t.W;
+    t.cs_base = tiled;
+    t.rs_base = tiled + cs;
+    t.floats = tiled + cs + rs;
 }
-// base pointer offset of a pixel (lane part only) and its row i within the owning thread's strip: weight s is at
-// base + aff_tiled_col_offset(s*R + i)
-__host__ __device__ __forceinline__ size_t aff_tiled_pixel_base(const AffTiling& t, int b, int y, int x, int* i_out) {
-    const int ty = y / (4 * t.R), ry = y % (4 * t.R), wq = ry / t.R;
-    *i_out = ry % t.R;
-    const size_t tile = ((size_t)b * t.tiles_y + ty) * t.tiles_x + (x >> 5);
-    return tile * ((size_t)48 * t.R * 128) + (size_t)(wq * 32 + (x & 31)) * 4;
+// Where the 48 weights of pixel (y, x) live: weight s is at base[s * stride] (row strip, stride > 0), at
+// base[aff_tiled_col_offset(s*R + i)] (tile pixels, stride == 0) or in the column strip's image (stride < 0).
+struct AffPixel {
+    size_t base;
+    int stride, i, R;
+    __host__ __device__ __forceinline__ size_t at(int s) const {
+        if (stride > 0) return base + (size_t)s * stride;
+        if (stride == 0) return base + aff_tiled_col_offset(s * R + i);
+        const int tpl = aff_cs_taps(R), part = s / tpl, k = s % tpl;  // base = block + lane of part 0
+        return base + (size_t)part * 4 + aff_tiled_col_offset(k);
+    }
+};
+__host__ __device__ __forceinline__ AffPixel aff_pixel(const AffTiling& t, int b, int y, int x) {
+    AffPixel p;
+    p.R = t.R;
+    p.i = 0;
+    const int ty4 = 4 * t.R;
+    if (y >= t.Ht) {  // row strip (including its corner with the column strip)
+        p.base = t.rs_base + ((size_t)b * (t.H - t.Ht) + (y - t.Ht)) * 48 * t.W + x;
+        p.stride = t.W;
+    } else if (x >= t.Wt) {  // column strip (one column)
+        const int ry = y % ty4;
+        p.base = t.cs_base + ((size_t)b * t.tiles_y + y / ty4) * aff_cs_block_floats(t.R) +
+                 (size_t)((ry / t.R) * 32 + (ry % t.R) * aff_cs_lanes(t.R)) * 4;
+        p.stride = -1;
+    } else {
+        const int ry = y % ty4, wq = ry / t.R;
+        const size_t tile = ((size_t)b * t.tiles_y + y / ty4) * t.tiles_x + (x >> 5);
+        p.base = tile * aff_tile_floats(t.R) + (size_t)(wq * 32 + (x & 31)) * 4;
+        p.stride = 0;
+        p.i = ry % t.R;
+    }
+    return p;
 }
 
 // Monotone float <-> unsigned map so that atomicMax(unsigned) implements a float max for any sign.
@@ -143,14 +185,6 @@ int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, co
                     const AffTiling& tiling, cudaStream_t s);
 int launch_aff_relayout(const float* aff_std, float* aff_tiled, int B, int H, int W, const AffTiling& tiling,
                         cudaStream_t s);
-// Second stream on which the column-strip kernel of iteration t runs concurrently with the tile kernel
-// of iteration t (both only depend on iteration t-1); two reusable events order the iterations.
-struct SideLane {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t tiles_done = nullptr;  // recorded on the main stream after each tile launch (and once before the first)
-    cudaEvent_t strip_done = nullptr;  // recorded on `stream` after each column-strip launch
-    bool strip_pending = false;        // strip_done holds a launch the main stream has not waited for yet
-};
 // Tiling of the tuned propagation kernel for this problem; R == 0 when only the generic kernel applies.
 AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil);
 size_t propagate_scratch_bytes(int B, int C, int H, int W, const Dilations& dil, int iters, bool aff_is_tiled);

@@ -18,8 +18,7 @@ namespace pamr {
 int pair_pitch(int W);
 int launch_repack_pairs(const float* src, float* dst, int planes, int H, int W, cudaStream_t s);
 int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, float* dst, int dst_pitch,
-                           bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s,
-                           SideLane* lane);
+                           bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s);
 
 namespace {
 
@@ -111,10 +110,10 @@ ScratchPlan plan_scratch(int B, int C, int H, int W, const Dilations& dil, int i
     if (iters <= 0) return p;
     const AffTiling t = tuned_tiling(B, H, W, dil);
     if (t.R > 0) {
-        // tuned kernel: two ping-pong buffers in the row-pair layout [B*C][ceil(H/2)][Wp][2], Wp even (TMA reads
-        // 64-bit elements and needs 16-byte global strides)
+        // tuned kernel: two ping-pong buffers in the row-pair layout [B*C][ceil(H/2)][Wp][2], Wp a multiple of 16
+        // (TMA reads 64-bit elements and needs 16-byte global strides; whole 128-byte lines per row pair)
         p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * ((H + 1) / 2) * pair_pitch(W) * 2, 256);
-        if (!aff_is_tiled) p.aff_tiled = align_up(sizeof(float) * aff_tiled_floats(B, t), 256);
+        if (!aff_is_tiled) p.aff_tiled = align_up(sizeof(float) * t.floats, 256);
     } else {
         p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * H * W, 256);
     }
@@ -123,12 +122,11 @@ ScratchPlan plan_scratch(int B, int C, int H, int W, const Dilations& dil, int i
 }
 
 // Per-thread, per-device side stream and events (created once, reused by every call of that thread): small
-// independent kernels (row-pair repack, remainder column strip) run on the side stream concurrently with the
-// big kernel on the caller's stream.  The persistent propagation kernel occupies every SM with one CTA but
-// leaves threads and registers for these, so their time disappears from the critical path.
+// independent kernel (the row-pair repack of the input mask) runs on the side stream concurrently with the
+// affinity kernel on the caller's stream, so its time disappears from the critical path.
 struct SideResources {
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_tiles = nullptr, ev_strip = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 int side_resources(int dev, SideResources** out) {
     static thread_local SideResources cache[64];
@@ -138,14 +136,11 @@ int side_resources(int dev, SideResources** out) {
         if (r == &overflow && r->side != nullptr) {  // device ordinals >= 64 share one slot: rebuild per call
             cudaStreamDestroy(r->side);
             cudaEventDestroy(r->ev_fork); cudaEventDestroy(r->ev_join);
-            cudaEventDestroy(r->ev_tiles); cudaEventDestroy(r->ev_strip);
             *r = SideResources();
         }
         PAMR_CUDA_TRY(cudaStreamCreateWithFlags(&r->side, cudaStreamNonBlocking));
         PAMR_CUDA_TRY(cudaEventCreateWithFlags(&r->ev_fork, cudaEventDisableTiming));
         PAMR_CUDA_TRY(cudaEventCreateWithFlags(&r->ev_join, cudaEventDisableTiming));
-        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&r->ev_tiles, cudaEventDisableTiming));
-        PAMR_CUDA_TRY(cudaEventCreateWithFlags(&r->ev_strip, cudaEventDisableTiming));
     }
     *out = r;
     return PAMR_OK;
@@ -247,8 +242,7 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
     }
 
     // ---- tuned kernel: the caller's mask is repacked into the row-pair layout on the side stream,
-    //      concurrently with the affinity / relayout kernel; the column strip of every iteration runs there too
-    const bool col_strip = tiling.Wt < W;
+    //      concurrently with the affinity / relayout kernel
     ForkJoin fj;
     if ((rc = fj.init(dev, s)) != PAMR_OK) return rc;
     if ((rc = fj.fork()) != PAMR_OK) return rc;
@@ -264,28 +258,17 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
     }
     if ((rc = fj.join()) != PAMR_OK) return rc;
 
-    SideLane lane;
-    if (col_strip) {
-        lane.stream = fj.r->side;
-        lane.tiles_done = fj.r->ev_tiles;
-        lane.strip_done = fj.r->ev_strip;
-        PAMR_CUDA_TRY(cudaEventRecord(lane.tiles_done, s));  // the first strip waits for affinity / repack
-        fj.forked = true;                                    // from here on the side stream carries strip launches
-    }
     const float* src = P[0];
     int next = 1;
     const int Wp = pair_pitch(W);
     for (int it = 0; it < iters; ++it) {
         const bool last = (it == iters - 1);
         float* dst = last ? m_out : P[next];
-        rc = launch_propagate_tuned(aff, tiling, src, dst, last ? W : Wp, !last, B, C, H, W, last ? cls_max : nullptr, dev,
-                                    s, col_strip ? &lane : nullptr);
+        rc = launch_propagate_tuned(aff, tiling, src, dst, last ? W : Wp, !last, B, C, H, W, last ? cls_max : nullptr, dev, s);
         if (rc != PAMR_OK) return rc;
         src = dst;
         next ^= 1;
     }
-    if (lane.strip_pending) PAMR_CUDA_TRY(cudaStreamWaitEvent(s, lane.strip_done, 0));  // join the last strip
-    fj.forked = false;
     return PAMR_OK;
 }
 

@@ -29,9 +29,10 @@
 //    clamped column offset, in y the consuming group patches the halo rows of top / bottom tiles;
 //  * FP32 math as packed FFMA2 over adjacent rows; the per-(b,c) max for pseudo_gtmask is fused into
 //    the last iteration (warp reduce + atomicMax);
-//  * remainders of at most 8 rows / columns (W = H = 321): the row strip is computed by the CTAs that
-//    are idle in the tile kernel's last wave (or a small launch when there are none), the column strip
-//    by a small kernel on a second stream, concurrently with the tile kernel.
+//  * remainders (W = H = 321 -> one column, one row): a column strip of at most 2 columns is computed by the
+//    tiles on the right image border from the window they hold anyway (one pixel per lane after every class
+//    pass, weights of the tile's strip pixels in shared memory); a row strip of at most 8 rows is computed by
+//    the CTAs that are idle in the kernel's last wave (or a small launch when there are none).
 #include <cuda.h>
 
 #include <atomic>
@@ -48,30 +49,49 @@ namespace {
 constexpr int TX = 32;
 constexpr int HALO = 24;
 constexpr int WIN_W = TX + 2 * HALO;  // 80 columns
-constexpr int ROWP = WIN_W * 2;       // floats per row PAIR of the window in shared memory
+// Pitch of the window in shared memory, in columns: 82, so that a row pair is 164 floats = 4 banks past a
+// multiple of 32 and the column strip's lanes (same column, different rows) fall on different banks (with 80
+// every row pair starts on the same bank).  TMA simply loads two more columns; nobody reads them.
+#ifndef PAMR_WIN_PAD
+#define PAMR_WIN_PAD 2
+#endif
+constexpr int WIN_P = WIN_W + PAMR_WIN_PAD;
+constexpr int ROWP = WIN_P * 2;       // floats per row PAIR of the window in shared memory
 constexpr int NW = 4;                 // warps per compute group (= TMEM lane quarters)
 constexpr int NG = 3;                 // compute groups that share the tile's weights in TMEM (class c -> group c % NG)
 constexpr int NWC = NG * NW;          // compute warps
-constexpr int NSLOT = 4;              // class-plane slots in the shared-memory ring
+#ifndef PAMR_NSLOT
+#define PAMR_NSLOT 4
+#endif
+#ifndef PAMR_NSTG
+#define PAMR_NSTG 3
+#endif
+#ifndef PAMR_PF_PLANES
+#define PAMR_PF_PLANES 0
+#endif
+constexpr int NSLOT = PAMR_NSLOT;     // class-plane slots in the shared-memory ring
 // mbarriers of the ring: sequence number n uses slot n % NSLOT but barrier pair n % NBAR.  Waits are by
 // phase PARITY, which is only sound if a waiter can never be a whole phase ahead of the barrier.  With one
 // barrier per slot and 4 slots, a group that has finished class k-3 tests the barrier of class k while the
 // load of class k-4 (same slot, other group) may -- once in ~1e7 passes -- still be in flight; the parity
 // test then reports the OLD phase as complete and the group computes on the wrong plane (round 1: 0.2-2.5 %
 // of the forward calls had one wrong tile-class; 0 of 5500 with 8 barrier pairs).
-constexpr int NBAR = 8;
+constexpr int NBAR = 2 * NSLOT;
 static_assert(NBAR % NSLOT == 0 && NBAR >= 2 * NSLOT, "barrier ring must cover at least two uses of every slot");
 // Warp roles: 0..11 compute, 12 class-plane producer (TMA), 13 weight loader (cp.async.bulk into the staging
 // ring), 14 and 15 weight issuers (tcgen05.cp staging -> TMEM; even / odd units).
 constexpr int W_PRODUCER = NWC, W_LOADER = NWC + 1, W_ISSUER = NWC + 2;
 constexpr int NTHREADS = (NWC + 4) * 32;
 constexpr int CHUNK_UNITS = 2;        // units handed over together ("chunk": 64 TMEM columns, 32 KB; the last chunk of a tile may be short)
-constexpr int NSTG = 3;               // staging ring for the weights: NSTG chunks of 32 KB
+constexpr int NSTG = PAMR_NSTG;       // staging ring for the weights: NSTG chunks of 32 KB
+constexpr int PF_PLANES = PAMR_PF_PLANES;  // class planes pulled into L2 this many classes ahead of their TMA load (0: off)
 constexpr int WB = 16;                // weights per tcgen05.ld batch of the centre column
 constexpr int UNIT = 32;              // TMEM columns per fill unit (= 2 batches)
 constexpr int UNIT_BYTES = UNIT * 128 * 4;  // 128 TMEM lanes
 constexpr int MAX_CHUNKS = 8;
 constexpr int CTRL_BYTES = 1024;
+constexpr int CS_MAX_W = 1;           // widest column strip the border tiles take on
+constexpr int RS_MAX_H = 8;           // tallest row strip
 
 __host__ __device__ constexpr int dil_of(int id) { return id == 0 ? 1 : id == 1 ? 2 : id == 2 ? 4 : id == 3 ? 8 : id == 4 ? 12 : 24; }
 
@@ -166,12 +186,17 @@ struct Cfg {
     static_assert(R % 2 == 0, "row pairs: R must be even");
     static constexpr int TY = NW * R;
     static constexpr int WIN_H = TY + 2 * HALO;  // even
-    static constexpr int SLOT_FLOATS = WIN_W * WIN_H;
-    static constexpr int SLOT_BYTES = SLOT_FLOATS * 4;
-    static constexpr size_t STAGE_OFF = (size_t)NSLOT * SLOT_BYTES;             // weight staging ring (1024-byte aligned)
-    static constexpr size_t CTRL_OFF = STAGE_OFF + (size_t)NSTG * CHUNK_UNITS * UNIT_BYTES;
+    static constexpr int SLOT_BYTES = WIN_P * WIN_H * 4;                      // what one TMA load brings
+    static constexpr int SLOT_FLOATS = (SLOT_BYTES + 127) / 128 * 32;         // slot stride: TMA destinations are 128-byte aligned
+    static constexpr size_t STAGE_OFF = (size_t)NSLOT * SLOT_FLOATS * 4;        // weight staging ring
+    static constexpr size_t CSW_OFF = STAGE_OFF + (size_t)NSTG * CHUNK_UNITS * UNIT_BYTES;  // staging of the column-strip weights
+    static constexpr int CS_LP = aff_cs_lanes(R), CS_TPL = aff_cs_taps(R);   // lanes per strip pixel, taps per lane
+    static constexpr int CSW_BYTES = (int)aff_cs_block_floats(R) * 4;
+    static constexpr int CS_COL0 = 48 * R;                                     // their TMEM columns [CS_COL0, CS_COL0 + CS_TPL)
+    static_assert(CS_TPL % 4 == 0 && CS_TPL <= WB && CS_COL0 + WB <= 512, "column-strip weights in spare TMEM columns");
+    static constexpr size_t CTRL_OFF = CSW_OFF + CSW_BYTES;
     static constexpr size_t SMEM_BYTES = CTRL_OFF + CTRL_BYTES;
-    static_assert(SLOT_BYTES % 128 == 0 && STAGE_OFF % 128 == 0, "TMA / bulk destinations");
+    static_assert(STAGE_OFF % 128 == 0, "TMA / bulk destinations");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
@@ -180,6 +205,9 @@ struct Ctrl {  // lives in the last CTRL_BYTES of dynamic shared memory
     unsigned long long empty_bar[NBAR];         // class plane consumed
     unsigned long long filled_bar[MAX_CHUNKS];  // the tile's weights of that chunk are in TMEM (tcgen05.commit)
     unsigned long long free_bar[MAX_CHUNKS];    // every compute warp has read the chunk for the last time in this tile
+    unsigned long long csw_staged_bar;          // column-strip weights of the next border tile have landed in shared memory
+    unsigned long long csw_full_bar;            // ... are in TMEM (tcgen05.commit)
+    unsigned long long csw_free_bar;            // ... and every compute warp is done with them
     unsigned long long staged_bar[2 * NSTG];    // the chunk's bytes have landed in the staging ring (chunk n: stage n % NSTG,
                                                 // barrier n % (2 NSTG), so that a barrier's consecutive phases belong to ONE issuer)
     uint32_t tmem_base;
@@ -187,16 +215,16 @@ struct Ctrl {  // lives in the last CTRL_BYTES of dynamic shared memory
 static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block");
 
 struct Params {
-    const float* aff;  // tile-major affinity (pamr_common.cuh), tiles_x_aff tile columns
-    const float* src;  // source mask, row-pair layout [B*C][Hp2][src_pitch][2] (the tiles read it through TMA, the strips directly)
+    const float* aff;  // affinity layout of pamr_common.cuh (tiles, column strip, row strip)
+    const float* src;  // source mask, row-pair layout [B*C][Hp2][src_pitch][2] (the tiles read it through TMA, the row strip directly)
     float* dst;        // dst_pair: row-pair layout [B*C][Hp2][dst_pitch][2]; else standard [B*C][H][dst_pitch]
     unsigned* cls_max; // [B,C] or nullptr
     int src_pitch, dst_pitch, dst_pair, Hp2;
     int pf_class;      // class index at whose TMA issue the prefetch of the next tile's weights into L2 starts
     int B, C, H, W;
-    int tiles_x, tiles_y, ntiles;  // tiles of this launch (tiles_x may exclude the remainder strip)
-    int tiles_x_aff, tiles_y_aff;  // tile grid of the affinity layout (covers the whole image)
+    int tiles_x, tiles_y, ntiles;  // tile grid (= the affinity layout's)
     int Wt, Ht;                    // the tiles cover [0,Wt) x [0,Ht)
+    size_t cs_base, rs_base;       // column-strip / row-strip weights inside aff
     int strip_items;               // number of 32-pixel row-strip work items
     int tail_cta0;                 // row strip inside the tile kernel: CTAs >= tail_cta0 (one tile fewer than the
                                    // others) work through the strip_items row items after their last tile; -1: off
@@ -418,54 +446,110 @@ __device__ __forceinline__ void patch_window(float* slot, int x0, int y0, int H,
         if (wx < WIN_W) {
             const int sx = min(max(wx, vx0), vx1 - 1);
             if (vy0 > 0) {
-                const float v = slot[pair_index(WIN_W, vy0, sx)];
-                for (int wy = wq; wy < vy0; wy += NW) slot[pair_index(WIN_W, wy, wx)] = v;
+                const float v = slot[pair_index(WIN_P, vy0, sx)];
+                for (int wy = wq; wy < vy0; wy += NW) slot[pair_index(WIN_P, wy, wx)] = v;
             }
             if (vy1 < WIN_H) {
-                const float v = slot[pair_index(WIN_W, vy1 - 1, sx)];
-                for (int wy = vy1 + wq; wy < WIN_H; wy += NW) slot[pair_index(WIN_W, wy, wx)] = v;
+                const float v = slot[pair_index(WIN_P, vy1 - 1, sx)];
+                for (int wy = vy1 + wq; wy < WIN_H; wy += NW) slot[pair_index(WIN_P, wy, wx)] = v;
             }
         }
     }
 }
 
-// Remainder strips.  The tiles cover [0,Wt) x [0,Ht); when W or H leaves a remainder of at most 8
-// pixels (W = H = 321 -> one column and one row) that remainder is not worth a tile row/column of
-// its own.  The row strip is cut into work items of 32 consecutive pixels of one row of one plane
-// (one pixel per lane, neighbours and weights straight from global memory / L2, clamped coordinates).
-template <int R>
-__device__ __forceinline__ void strip_item(const Params& prm, const int Wt, int item, int lane) {
+// Row strip.  The tiles cover [0,Wt) x [0,Ht); a remainder of at most RS_MAX_H rows (H = 321 -> one row) is not
+// worth a tile row of its own.  It is cut into work items of 32 consecutive pixels of one row of one plane (one
+// pixel per lane, neighbours straight from global memory / L2 with clamped coordinates, weights from the
+// row-strip region of the affinity layout: coalesced).  The strip spans ALL columns, including its corner with
+// the column strip.
+__device__ __forceinline__ void strip_item(const Params& prm, int item, int lane) {
     const int C = prm.C, H = prm.H, W = prm.W;
-    const int wcols = W - Wt, hrows = H - prm.Ht;
-    const int yblocks = (H + 31) / 32, xblocks = (Wt + 31) / 32;
-    const int per_plane = wcols * yblocks + hrows * xblocks;
+    const int hrows = H - prm.Ht, xblocks = (W + 31) / 32;
+    const int per_plane = hrows * xblocks;
     const int plane = item / per_plane, r = item % per_plane;  // plane = b*C + c
-    int x, y;
-    if (r < wcols * yblocks) {
-        x = Wt + r / yblocks;
-        y = (r % yblocks) * 32 + lane;
-    } else {
-        const int q = r - wcols * yblocks;
-        y = prm.Ht + q / xblocks;
-        x = (q % xblocks) * 32 + lane;
-        if (x >= Wt) x = W;  // beyond the row strip (those columns belong to the column strip)
-    }
-    const bool valid = (y < H) && (x < W);
-    const int yc = min(y, H - 1), xc = min(x, W - 1);
+    const int yi = r / xblocks, y = prm.Ht + yi, x = (r % xblocks) * 32 + lane;
+    const bool valid = x < W;
+    const int xc = min(x, W - 1);
     const int b = plane / C;
     const float* __restrict__ pl = prm.src + (size_t)plane * src_plane_stride(prm);
-    const AffTiling tl{R, prm.tiles_x_aff, prm.tiles_y_aff, 0, 0};
-    int wi = 0;
-    const float* __restrict__ wp = prm.aff + aff_tiled_pixel_base(tl, b, yc, xc, &wi);
+    const float* __restrict__ wp = prm.aff + prm.rs_base + ((size_t)b * hrows + yi) * 48 * W + xc;
     float acc = 0.f;  // one FMA chain in tap-sequence order: bit-identical to the tile kernel's result
 #pragma unroll
     for (int s = 0; s < 48; ++s) {
         const int p = seq_tap(s), d = dil_of(p >> 3), j = p & 7;
-        const int yy = clampi(yc + tap_dy(j) * d, 0, H - 1);
+        const int yy = clampi(y + tap_dy(j) * d, 0, H - 1);
         const int xx = clampi(xc + tap_dx(j) * d, 0, W - 1);
-        acc = fmaf(__ldg(wp + aff_tiled_col_offset(s * R + wi)), __ldg(pl + pair_index(prm.src_pitch, yy, xx)), acc);
+        acc = fmaf(__ldg(wp + (size_t)s * W), __ldg(pl + pair_index(prm.src_pitch, yy, xx)), acc);
     }
     if (valid) *dst_pixel(prm, plane, y, x) = acc;
+    if (prm.cls_max != nullptr) {
+        const unsigned m = __reduce_max_sync(0xffffffffu, valid ? ordered_from_float(acc) : 0u);
+        if (lane == 0 && m != 0u) atomicMax(prm.cls_max + plane, m);
+    }
+}
+
+// Offsets (floats) of the 48 neighbours of a column-strip pixel relative to the pixel itself inside the window, in
+// tap-sequence order, for even / odd window rows: dy even moves whole row pairs, dy = +-1 depends on the row's
+// parity; dx < 0 moves left; replicate padding clamps every dx > 0 tap to the strip column itself (it is image
+// column W-1).  Constant-initialised: no upload.
+struct CsOffsets {
+    int off[2][48];
+};
+constexpr CsOffsets make_cs_offsets() {
+    CsOffsets t{};
+    for (int par = 0; par < 2; ++par)
+        for (int s = 0; s < 48; ++s) {
+            const int p = seq_tap(s), d = dil_of(p >> 3), j = p & 7;
+            const int ty = (j < 3) ? -1 : (j < 5 ? 0 : 1);
+            const int tx = (j == 0 || j == 3 || j == 5) ? -1 : ((j == 1 || j == 6) ? 0 : 1);
+            int o = 0;
+            if (ty != 0) o += (d != 1) ? ty * (d / 2) * ROWP : (ty < 0 ? (par ? -1 : 1 - ROWP) : (par ? ROWP - 1 : 1));
+            if (tx < 0) o -= 2 * d;
+            t.off[par][s] = o;
+        }
+    return t;
+}
+__constant__ CsOffsets c_cs = make_cs_offsets();
+
+// Column strip x = Wt = W-1, computed by the tiles on the right image border (x0 + 32 == Wt) after every class
+// pass from the window the warp just used (rows outside the image have been patched).  LP = 32/R lanes share a
+// strip pixel: lane i*LP + part of warp wq takes taps [part*TPL, (part+1)*TPL) of pixel (row wq*R + i of the tile);
+// the parts run one after the other on the same accumulator (handed on by shuffle), i.e. ONE FMA chain in
+// tap-sequence order, bit-identical to every other path.  The lane's TPL weights come from its spare TMEM columns
+// (one tcgen05.ld), so the pass costs only TPL shared-memory loads per warp: LSU instructions, not bytes, are
+// what a warp on this kernel's saturated shared-memory pipe waits for.
+#ifndef PAMR_CS_INLINE
+#define PAMR_CS_INLINE __forceinline__
+#endif
+template <int R>
+__device__ PAMR_CS_INLINE void column_strip_pass(const Params& prm, const float* __restrict__ slot, uint32_t tbase, int plane,
+                                                  int y0, int wq, int lane) {
+    constexpr int LP = Cfg<R>::CS_LP, TPL = Cfg<R>::CS_TPL;
+    const int part = lane % LP, i = min(lane / LP, R - 1);
+    const bool active = lane < R * LP;
+    const int row = wq * R + i, wy = row + HALO;
+    const float* __restrict__ v0 = slot + pair_index(WIN_P, wy, TX + HALO);
+    const int* __restrict__ offs = c_cs.off[wy & 1] + part * TPL;
+    float w[WB], v[TPL];
+    tmem_ld16(tbase + Cfg<R>::CS_COL0, w);
+#pragma unroll
+    for (int k = 0; k < TPL; ++k) v[k] = v0[offs[k]];
+    tmem_wait_ld(w);
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < LP; ++r) {
+        if (part == r) {
+#pragma unroll
+            for (int k = 0; k < TPL; ++k) acc = fmaf(w[k], v[k], acc);
+        }
+        if (r + 1 < LP) {
+            const float t = __shfl_up_sync(0xffffffffu, acc, 1);
+            if (part == r + 1) acc = t;
+        }
+    }
+    const int y = y0 + row;
+    const bool valid = active && part == LP - 1 && y < prm.H;
+    if (valid) *dst_pixel(prm, plane, y, prm.Wt) = acc;
     if (prm.cls_max != nullptr) {
         const unsigned m = __reduce_max_sync(0xffffffffu, valid ? ordered_from_float(acc) : 0u);
         if (lane == 0 && m != 0u) atomicMax(prm.cls_max + plane, m);
@@ -480,6 +564,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* slots = reinterpret_cast<float*>(smem_raw);
     unsigned char* stage_ring = smem_raw + C_::STAGE_OFF;
+    const int wc = prm.W - prm.Wt;  // column strip width (0: none)
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem_raw + C_::CTRL_OFF);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = prm.C, H = prm.H, W = prm.W;
@@ -495,6 +580,9 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             mbar_init(smem_u32(&ctrl->free_bar[u]), NW * active_groups);   // every compute warp that reads weights
         }
         for (int g = 0; g < 2 * NSTG; ++g) mbar_init(smem_u32(&ctrl->staged_bar[g]), 1);
+        mbar_init(smem_u32(&ctrl->csw_staged_bar), 1);
+        mbar_init(smem_u32(&ctrl->csw_full_bar), 1);
+        mbar_init(smem_u32(&ctrl->csw_free_bar), NW * active_groups);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -512,7 +600,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
     auto tile_weights = [&](int ti) -> const float* {
         const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
         const int b = tile / tiles_per_img, t = tile % tiles_per_img;
-        return prm.aff + (((size_t)b * prm.tiles_y_aff + t / prm.tiles_x) * prm.tiles_x_aff + t % prm.tiles_x) * ((size_t)48 * R * 128);
+        return prm.aff + (((size_t)b * prm.tiles_y + t / prm.tiles_x) * prm.tiles_x + t % prm.tiles_x) * aff_tile_floats(R);
     };
 
     if (warp == W_PRODUCER) {
@@ -539,7 +627,15 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 mbar_arrive_expect_tx(bar, C_::SLOT_BYTES);
                 // 64-bit elements = row pairs: coordinates (column, row pair, plane)
                 tma_load_3d(smem_u32(slots + (size_t)s * C_::SLOT_FLOATS), &tmap, bar, x0 - HALO, (y0 - HALO) / 2, b * C + c);
-                PAMR_EV(3 + 2, false, 1000 + n_issue);
+                if (PF_PLANES > 0 && n_issue + PF_PLANES < total) {  // pull a later plane window from HBM into L2
+                    const long long np = n_issue + PF_PLANES;
+                    const int pti = (int)(np / C), pc = (int)(np % C);
+                    const int ptile = (int)blockIdx.x + pti * (int)gridDim.x;
+                    const int pb = ptile / tiles_per_img, pt = ptile % tiles_per_img;
+                    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                                 ::"l"(&tmap), "r"((pt % prm.tiles_x) * TX - HALO), "r"(((pt / prm.tiles_x) * C_::TY - HALO) / 2), "r"(pb * C + pc)
+                                 : "memory");
+                }
             }
             // Late in a tile, pull the NEXT tile's affinity weights (one contiguous 48*R*128-byte block
             // per lane quarter of the tile-major layout) from HBM into L2, one quarter per class, so that
@@ -560,8 +656,21 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         if (lane == 0) {
             const int total = my_tiles * L::NCH;
             [[maybe_unused]] int ev_n = 0;
+            int cs_uses = 0;  // border tiles of this CTA so far
             for (int n = 0; n < total; ++n) {
                 const int ti = n / L::NCH, c = n % L::NCH, g = n % NSTG;
+                if (c == 0 && wc > 0) {  // a tile on the right image border: its column-strip weights -> shared memory
+                    const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                    const int b = tile / tiles_per_img, t = tile % tiles_per_img;
+                    if (t % prm.tiles_x == prm.tiles_x - 1) {
+                        if (cs_uses > 0) mbar_wait(smem_u32(&ctrl->csw_full_bar), (uint32_t)(cs_uses - 1) & 1u);  // the staging area has been read
+                        const uint32_t bar = smem_u32(&ctrl->csw_staged_bar);
+                        mbar_arrive_expect_tx(bar, C_::CSW_BYTES);
+                        bulk_load(smem_u32(smem_raw + C_::CSW_OFF),
+                                  prm.aff + prm.cs_base + ((size_t)b * prm.tiles_y + t / prm.tiles_x) * aff_cs_block_floats(R), C_::CSW_BYTES, bar);
+                        ++cs_uses;
+                    }
+                }
                 if (n >= NSTG) {
                     const int pn = n - NSTG;
                     mbar_wait(smem_u32(&ctrl->filled_bar[pn % L::NCH]), (uint32_t)(pn / L::NCH) & 1u);
@@ -584,8 +693,23 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             int n = warp - W_ISSUER;
             static_assert(L::NCH % 2 == 0, "a chunk index must always meet the same issuer (mbarrier waits are by phase parity)");
             if (n < total) mbar_wait(smem_u32(&ctrl->staged_bar[n % (2 * NSTG)]), (uint32_t)(n / (2 * NSTG)) & 1u);  // bytes landed
+            int cs_uses = 0;  // border tiles of this CTA so far
             for (; n < total; n += 2) {
                 const int ti = n / L::NCH, c = n % L::NCH, g = n % NSTG;
+                if (c == 0 && wc > 0) {  // (chunk 0 always meets issuer 0) a border tile: its strip weights -> spare TMEM columns
+                    const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                    if ((tile % tiles_per_img) % prm.tiles_x == prm.tiles_x - 1) {
+                        mbar_wait(smem_u32(&ctrl->csw_staged_bar), (uint32_t)cs_uses & 1u);
+                        if (cs_uses > 0) mbar_wait(smem_u32(&ctrl->csw_free_bar), (uint32_t)(cs_uses - 1) & 1u);  // previous border tile done
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem_raw + C_::CSW_OFF);
+#pragma unroll
+                        for (int k = 0; k < C_::CS_TPL / 4; ++k)  // 4 columns each: 128 lanes x 16 bytes
+                            asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(tb + C_::CS_COL0 + k * 4), "l"(utccp_desc(sa + k * 2048, 0, 128)) : "memory");
+                        utccp_commit(smem_u32(&ctrl->csw_full_bar));
+                        ++cs_uses;
+                    }
+                }
                 if (ti > 0) mbar_wait(smem_u32(&ctrl->free_bar[c]), (uint32_t)(ti - 1) & 1u);  // the previous tile's last passes have read the chunk
                 tc_fence_after();
                 PAMR_EV(4, warp == W_ISSUER, 2100 + c);
@@ -604,6 +728,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         const int grp = warp / NW, wq = warp % NW;  // wq = TMEM lane quarter; all groups share the weights
         const uint32_t tbase = ctrl->tmem_base + ((uint32_t)(wq * 32) << 16);
         const uint32_t filled0 = smem_u32(&ctrl->filled_bar[0]), free0 = smem_u32(&ctrl->free_bar[0]);
+        int cs_seen = 0;  // border tiles of this CTA so far
         [[maybe_unused]] int ev_n = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
@@ -614,6 +739,12 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             const long long seq0 = (long long)ti * C;
             const bool border = needs_patch<R>(y0, H);
             const int nrow = xok ? max(0, min(R, H - yw)) : 0;  // rows of this thread inside the image
+            const bool cs_tile = wc > 0 && (t % prm.tiles_x == prm.tiles_x - 1);  // this tile also computes the column strip
+            if (cs_tile && grp < C) {
+                mbar_wait(smem_u32(&ctrl->csw_full_bar), (uint32_t)cs_seen & 1u);  // its strip weights are in TMEM
+                tc_fence_after();
+                ++cs_seen;
+            }
 
             int probe = 0;  // 1: the barriers of this group's next class were already seen complete
             for (int k = grp; k < C; k += NG) {
@@ -642,6 +773,14 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 const bool first = (k == grp), last = (k + NG >= C);
 #endif
                 compute_pass<R>(sp, tbase, acc, x, W, first ? filled0 : 0u, last ? free0 : 0u, (uint32_t)ti & 1u, lane);
+                if (cs_tile) {
+                    column_strip_pass<R>(prm, slot, tbase, b * C + k, y0, wq, lane);
+                    if (last) {  // this warp is done with the tile's strip weights
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&ctrl->csw_free_bar));
+                    }
+                }
                 PAMR_EV(grp, wq == 0 && lane == 0, 9);
                 // release the slot as early as possible
                 __syncwarp();
@@ -690,7 +829,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         if (prm.tail_cta0 >= 0 && (int)blockIdx.x >= prm.tail_cta0) {
             const int nw = ((int)gridDim.x - prm.tail_cta0) * NWC;
             for (int item = ((int)blockIdx.x - prm.tail_cta0) * NWC + warp; item < prm.strip_items; item += nw)
-                strip_item<R>(prm, W, item, lane);
+                strip_item(prm, item, lane);
         }
     }
 
@@ -700,84 +839,11 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(ctrl->tmem_base), "r"(512));
 }
 
-// ---- remainder strips as small kernels (row strip: only when the tile kernel's last wave has no idle CTAs) ----
-// (Alternatives measured on B200 in round 1 and rejected: the same work inside the persistent kernel by the
-//  producer warp or by the compute warps at every tile boundary; the remainder column fused into the last
-//  full tile column -- a bank-conflicted extra pass; partial tiles cost a whole tile column.)
-
-// Row strip: y in [Ht,H), all x.  One warp per 32 consecutive pixels of a row (coalesced).
-template <int R>
+// Row strip as a launch of its own: only when the tile kernel's last wave has no idle CTAs for it.
 __global__ void __launch_bounds__(128) strip_rows_kernel(const Params prm) {
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < prm.strip_items; item += gridDim.x * wpb)
-        strip_item<R>(prm, prm.Wt, item, lane);
-}
-
-// Column strip: x in [Wt,W), all y.  Neighbours of a column of pixels lie in different rows, i.e.
-// in different cache lines, so one CTA stages the last 32 columns of 32 + 48 rows of the class planes in
-// shared memory with coalesced row reads (one warp per class plane), then every warp computes 32 pixels
-// (lane = row) x (W-Wt) columns of its class from shared memory.
-constexpr int SC_ROWS = 32;                      // pixel rows per CTA
-constexpr int SC_WIN_H = SC_ROWS + 2 * HALO;     // 80
-constexpr int SC_WIN_W = 32;                     // staged columns [W-32, W)  (needs W >= 32)
-constexpr int SC_LOADS = 20;                     // row loads in flight per thread while staging (SC_WIN_H % SC_LOADS == 0)
-constexpr int SC_CG = 8;                         // class planes staged at a time (one warp each)
-constexpr int SC_MAX_WC = 8;                     // widest column strip (shared-memory weights, window columns)
-template <int R>
-__global__ void __launch_bounds__(SC_CG * 32, 5) strip_cols_kernel(const Params prm) {  // (.,5): <= 48 registers, so that a CTA fits next to a resident tile CTA
-    extern __shared__ float sc_smem[];  // [SC_CG][SC_WIN_H][SC_WIN_W + 1] then weights [wc][48][32]
-    const int C = prm.C, H = prm.H, W = prm.W, wc = W - prm.Wt;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int yb = blockIdx.x * SC_ROWS, b = blockIdx.y;
-    constexpr int PITCH = SC_WIN_W + 1;
-    float* wsm = sc_smem + (size_t)SC_CG * SC_WIN_H * PITCH;
-    const int xs0 = W - SC_WIN_W;  // first staged column
-    // the weights of the strip pixels: wsm[(xi*48 + s)*32 + row]
-    const AffTiling tl{R, prm.tiles_x_aff, prm.tiles_y_aff, 0, 0};
-    for (int e = threadIdx.x; e < wc * 48 * SC_ROWS; e += blockDim.x) {
-        const int row = e % SC_ROWS, s = (e / SC_ROWS) % 48, xi = e / (SC_ROWS * 48);
-        wsm[e] = __ldg(prm.aff + aff_tiled_index(tl, b, s, min(yb + row, H - 1), prm.Wt + xi));
-    }
-    const int y = yb + lane;
-    float* mywin = sc_smem + (size_t)warp * SC_WIN_H * PITCH;
-    for (int c0 = 0; c0 < C; c0 += SC_CG) {
-        const int c = c0 + warp;
-        if (c < C) {  // stage this warp's class plane window (rows clamped: replicate padding)
-            const float* __restrict__ pl = prm.src + ((size_t)b * C + c) * src_plane_stride(prm);
-            // SC_LOADS row loads in flight at a time: the kernel overlaps the tile kernel on a second stream and is
-            // kept at <= 48 registers so that its CTAs can be placed next to a resident tile CTA
-#pragma unroll 1
-            for (int r0 = 0; r0 < SC_WIN_H; r0 += SC_LOADS) {
-                float v[SC_LOADS];
-#pragma unroll
-                for (int q = 0; q < SC_LOADS; ++q)
-                    v[q] = __ldg(pl + pair_index(prm.src_pitch, clampi(yb - HALO + r0 + q, 0, H - 1), xs0 + lane));
-#pragma unroll
-                for (int q = 0; q < SC_LOADS; ++q) mywin[(r0 + q) * PITCH + lane] = v[q];
-            }
-        }
-        __syncthreads();  // also covers the weights on the first round
-        if (c < C) {
-            const float* win = mywin + (lane + HALO) * PITCH;
-            for (int xi = 0; xi < wc; ++xi) {
-                const int xl = prm.Wt + xi - xs0;  // column inside the staged window (>= 24: wc <= SC_MAX_WC)
-                float acc = 0.f;  // tap-sequence order, like the tile kernel (bit-identical results)
-#pragma unroll
-                for (int sq = 0; sq < 48; ++sq) {
-                    const int p = seq_tap(sq), d = dil_of(p >> 3), j = p & 7;
-                    const int xx = min(xl + tap_dx(j) * d, SC_WIN_W - 1);  // clamp at the right image border
-                    acc = fmaf(wsm[(xi * 48 + sq) * SC_ROWS + lane], win[tap_dy(j) * d * PITCH + xx], acc);
-                }
-                const bool valid = y < H;
-                if (valid) *dst_pixel(prm, b * C + c, y, prm.Wt + xi) = acc;
-                if (prm.cls_max != nullptr) {
-                    const unsigned m = __reduce_max_sync(0xffffffffu, valid ? ordered_from_float(acc) : 0u);
-                    if (lane == 0 && m != 0u) atomicMax(prm.cls_max + (size_t)b * C + c, m);
-                }
-            }
-        }
-        __syncthreads();
-    }
+        strip_item(prm, item, lane);
 }
 
 // Copy [planes,H,W] -> row-pair layout [planes,Hp2,Wp,2] (TMA reads 64-bit elements; Wp even keeps its
@@ -817,7 +883,7 @@ int make_tmap(CUtensorMap* map, const float* base, int planes, int Hp2, int Wp, 
     if (fn == nullptr) return set_error(PAMR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[3] = {(cuuint64_t)Wp, (cuuint64_t)Hp2, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)Wp * 8, (cuuint64_t)Wp * 8 * (cuuint64_t)Hp2};
-    cuuint32_t box[3] = {(cuuint32_t)WIN_W, (cuuint32_t)(win_h / 2), 1};
+    cuuint32_t box[3] = {(cuuint32_t)WIN_P, (cuuint32_t)(win_h / 2), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<float*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -849,18 +915,16 @@ int device_sm_count(int dev, int* out) {
 
 template <int R>
 int launch_one(const float* aff, const AffTiling& tiling, const float* src, int src_pitch, float* dst, int dst_pitch,
-               bool dst_pair, int B, int C, int H, int W, int Wt, int Ht, unsigned* cls_max, int sm_count, int dev,
-               cudaStream_t s, SideLane* lane) {
+               bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int sm_count, int dev, cudaStream_t s) {
     using C_ = Cfg<R>;
     // function attributes are per device: set once per (kernel, device)
     static std::atomic<int> attr_set[64];
     if (dev < 0 || dev >= 64 || attr_set[dev].load(std::memory_order_acquire) == 0) {
         PAMR_CUDA_TRY(cudaFuncSetAttribute(propagate_sm100_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)C_::SMEM_BYTES));
-        PAMR_CUDA_TRY(cudaFuncSetAttribute(strip_cols_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         if (dev >= 0 && dev < 64) attr_set[dev].store(1, std::memory_order_release);
     }
-    const int Hp2 = (H + 1) / 2;
+    const int Hp2 = (H + 1) / 2, Wt = tiling.Wt, Ht = tiling.Ht;
     alignas(64) CUtensorMap tmap;
     int rc = make_tmap(&tmap, src, B * C, Hp2, src_pitch, C_::WIN_H);
     if (rc != PAMR_OK) return rc;
@@ -869,11 +933,10 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
     p.src_pitch = src_pitch; p.dst_pitch = dst_pitch; p.dst_pair = dst_pair ? 1 : 0; p.Hp2 = Hp2;
     p.pf_class = C >= 8 ? C - 8 : 0;
     p.B = B; p.C = C; p.H = H; p.W = W;
-    p.tiles_x = (Wt + TX - 1) / TX;
-    p.tiles_y = (Ht + C_::TY - 1) / C_::TY;
-    p.tiles_x_aff = tiling.tiles_x;
-    p.tiles_y_aff = tiling.tiles_y;
+    p.tiles_x = tiling.tiles_x;
+    p.tiles_y = tiling.tiles_y;
     p.Wt = Wt; p.Ht = Ht;
+    p.cs_base = tiling.cs_base; p.rs_base = tiling.rs_base;
     p.strip_items = 0;
     p.tail_cta0 = -1;
 #ifdef PAMR_EXPERIMENTS
@@ -885,49 +948,22 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
     if (ntiles > 0x7fffffffLL) return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: too many tiles");
     p.ntiles = (int)ntiles;
     const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
-    const bool col_strip = Wt < W;
-    if (col_strip && lane != nullptr && lane->strip_pending) {  // this iteration reads what strip(t-1) wrote
-        PAMR_CUDA_TRY(cudaStreamWaitEvent(s, lane->strip_done, 0));
-        lane->strip_pending = false;
-    }
     const long long row_items = (long long)B * C * (H - Ht) * ((W + 31) / 32);
     if (row_items > 0x7fffffffLL) return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: row strip too large");
     if (Ht < H && row_strip_in_tail(row_items, ntiles, grid)) {
         p.strip_items = (int)row_items;  // the tile kernel's short CTAs do the row strip
         p.tail_cta0 = p.ntiles % grid;
-    } else if (Ht < H) {  // row strip y in [Ht,H), all columns, as a launch of its own
+    } else if (Ht < H) {  // row strip y in [Ht,H) as a launch of its own (reads iteration t-1 like the tiles)
         Params pr = p;
-        pr.Wt = W;  // strip_item: no column part, the row part spans [0,W)
         pr.strip_items = (int)row_items;
         const int blocks = (int)((row_items + 3) / 4);
-        strip_rows_kernel<R><<<blocks < 8 * sm_count ? blocks : 8 * sm_count, 128, 0, s>>>(pr);
+        strip_rows_kernel<<<blocks < 8 * sm_count ? blocks : 8 * sm_count, 128, 0, s>>>(pr);
         count_launch();
         PAMR_CUDA_TRY(cudaGetLastError());
     }
-    // The column strip (x in [Wt,W), all rows) runs on the side lane concurrently with the tile kernel:
-    // both only read iteration t-1.  Its CTAs mostly get placed as tile CTAs retire in the last wave,
-    // which hides about half of it.  Ordering: the main stream waited for strip(t-1) above
-    // (iteration t reads and overwrites what that strip wrote / read); strip(t) waits for tiles(t-1).
     propagate_sm100_kernel<R><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, p);
     count_launch();
     PAMR_CUDA_TRY(cudaGetLastError());
-    if (col_strip) {
-        const size_t smem = sizeof(float) * ((size_t)SC_CG * SC_WIN_H * (SC_WIN_W + 1) + (size_t)(W - Wt) * 48 * SC_ROWS);
-        dim3 sgrid((H + SC_ROWS - 1) / SC_ROWS, B);
-        cudaStream_t ss = s;
-        if (lane != nullptr) {
-            ss = lane->stream;
-            PAMR_CUDA_TRY(cudaStreamWaitEvent(ss, lane->tiles_done, 0));  // tiles(t-1) (or the prologue) finished
-        }
-        strip_cols_kernel<R><<<sgrid, SC_CG * 32, smem, ss>>>(p);
-        count_launch();
-        PAMR_CUDA_TRY(cudaGetLastError());
-        if (lane != nullptr) {
-            PAMR_CUDA_TRY(cudaEventRecord(lane->strip_done, ss));
-            lane->strip_pending = true;
-            PAMR_CUDA_TRY(cudaEventRecord(lane->tiles_done, s));  // tiles(t), for strip(t+1)
-        }
-    }
     return PAMR_OK;
 }
 
@@ -943,22 +979,21 @@ extern "C" void pamr_debug_set_timeline(long long* dev_buf, int cta, int skip) {
 }
 #endif
 
-// Tiling of the tuned kernel (R rows per thread, tile = 32 x 4R, extent [0,Wt) x [0,Ht) covered by
-// tiles) or R == 0 when the tuned kernel does not apply.  Remainders of at most 8 rows / columns have
-// an alternative to a padded tile row / partial tile column:
-//   rows:    the row strip -- inside the tile kernel's last wave when that wave has idle CTAs
-//            (row_strip_in_tail), else a launch of its own;
-//   columns: the column-strip launch.
-// All combinations with R in {8,10} are priced with a time model fitted to measurements on B200
-// (profiles/r01_strip_times.txt): waves of tiles over the SMs at a cost per row-per-thread, row-strip
-// launch ~ 8 + 1.3 us per 1000 items, column-strip launch ~ (12 + 2.6 wc) * max(1, CTAs/90)^0.8 us minus
-// what hides in the last wave -- and the cheapest wins.  E.g. 321 x 321, B=16: R=10, 10 x 8 tiles, row 320
-// in the tail of the same launch, column 320 as a strip launch on the side lane.  All paths add the 48
-// products of a pixel in the same order, so the result does not depend on the tiling (nor, therefore, on
-// how a batch is sharded).  The model prices the reference's 21 classes; the SM count is the current device's.
+// Tiling of the tuned kernel (R rows per thread, tile = 32 x 4R, extent [0,Wt) x [0,Ht) covered by tiles) and
+// the affinity layout that goes with it, or R == 0 when the tuned kernel does not apply.  Remainders have an
+// alternative to a padded tile row / partial tile column:
+//   rows (<= RS_MAX_H):    the row strip -- inside the tile kernel's last wave when that wave has idle CTAs
+//                          (row_strip_in_tail), else a launch of its own;
+//   columns (<= CS_MAX_W): the column strip, computed by the tiles on the right image border.
+// All combinations with R in {8,10} are priced with a time model fitted to measurements on B200 -- waves of
+// tiles over the SMs at a cost per row-per-thread, border tiles a little dearer per strip column, row-strip
+// launch ~ 8 + 1.3 us per 1000 items -- and the cheapest wins.  E.g. 321 x 321, B=16: R=10, 10 x 8 tiles, column
+// 320 by the border tiles, row 320 in the tail of the same launch.  All paths add the 48 products of a pixel in
+// the same order, so the result does not depend on the tiling (nor, therefore, on how a batch is sharded).  The
+// model prices the reference's 21 classes; the SM count is the current device's.
 AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
     static const int want[6] = {1, 2, 4, 8, 12, 24};
-    AffTiling t{0, 0, 0, 0, 0};
+    AffTiling t{};
     if (dil.nd != 6 || W < TX || H < 8) return t;
     for (int i = 0; i < 6; ++i)
         if (dil.d[i] != want[i]) return t;
@@ -968,17 +1003,18 @@ AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
     double best_cost = 1e30;
     for (int r = 8; r <= 10; r += 2) {
         const int ty = NW * r;
-        const double tile_us = 2.0 * r * (r == 10 ? 1.00 : 1.07);
+        const double tile_us = 1.8 * r * (r == 10 ? 1.00 : 1.07);
         const int hrem = H % ty, wrem = W % TX;
-        const bool rs_ok = hrem != 0 && hrem <= SC_MAX_WC && H > ty;
-        const bool cs_ok = wrem != 0 && wrem <= SC_MAX_WC && W > TX;
+        const bool rs_ok = hrem != 0 && hrem <= RS_MAX_H && H > ty;
+        const bool cs_ok = wrem != 0 && wrem <= CS_MAX_W && W > TX;
         for (int rs = 0; rs < 2; ++rs) {      // rs: row remainder as a strip
             if (rs && !rs_ok) continue;
             const int ht = rs ? H - hrem : H;
-            for (int cs = 0; cs < 2; ++cs) {  // cs: column remainder as a strip launch
+            for (int cs = 0; cs < 2; ++cs) {  // cs: column remainder as a strip of the border tiles
                 if (cs && !cs_ok) continue;
                 const int wt = cs ? W - wrem : W;
-                const long long ntiles = (long long)B * ((wt + TX - 1) / TX) * ((ht + ty - 1) / ty);
+                const int txs = (wt + TX - 1) / TX, tys = (ht + ty - 1) / ty;
+                const long long ntiles = (long long)B * txs * tys;
                 if (ntiles > 0x7fffffffLL) continue;
                 double cost = (double)((ntiles + sms - 1) / sms) * tile_us;
                 if (rs) {
@@ -986,30 +1022,23 @@ AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
                     const int grid = ntiles < sms ? (int)ntiles : sms;
                     if (!row_strip_in_tail(items, ntiles, grid)) cost += 8.0 + 1.3e-3 * (double)items;
                 }
-                if (cs) {
-                    const double ctas = (double)B * ((H + SC_ROWS - 1) / SC_ROWS);
-                    // stand-alone duration, less what hides in the idle part of the tile kernel's last wave
-                    // (the strip runs on the side lane and its CTAs land on SMs whose tile CTA has retired)
-                    const double alone = (12.0 + 2.6 * wrem) * pow(ctas > 90.0 ? ctas / 90.0 : 1.0, 0.8);
-                    const double waves = (double)((ntiles + sms - 1) / sms);
-                    const double idle_us = (waves * sms - (double)ntiles) / sms * tile_us;
-                    cost += fmax(0.25 * alone, alone - 0.85 * idle_us);
-                }
+                if (cs) cost *= 1.0 + 0.1 / txs;  // one tile in txs also does the strip column
                 if (cost < best_cost) {
                     best_cost = cost;
-                    t.R = r; t.Wt = wt; t.Ht = ht;
+                    t.R = r; t.Wt = wt; t.Ht = ht; t.tiles_x = txs; t.tiles_y = tys;
                 }
             }
         }
     }
     if (t.R == 0) return t;  // nothing fits (gigantic B*H*W): the generic kernel takes it
-    t.tiles_x = (W + TX - 1) / TX;
-    t.tiles_y = (H + NW * t.R - 1) / (NW * t.R);
+    t.W = W; t.H = H;
+    aff_layout_finish(t, B);
     return t;
 }
 
-// pitch (in 64-bit elements) of the row-pair layout for image width W
-int pair_pitch(int W) { return (W + 1) / 2 * 2; }
+// pitch (in 64-bit elements) of the row-pair layout for image width W: whole 128-byte lines per row pair, so that
+// the rows TMA fetches and the rows the warps store start on line boundaries for any W
+int pair_pitch(int W) { return (W + 15) / 16 * 16; }
 
 int launch_repack_pairs(const float* src, float* dst, int planes, int H, int W, cudaStream_t s) {
     const int Hp2 = (H + 1) / 2, Wp = pair_pitch(W);
@@ -1021,22 +1050,21 @@ int launch_repack_pairs(const float* src, float* dst, int planes, int H, int W, 
     return PAMR_OK;
 }
 
-// One propagation step src -> dst: the strip kernels (if the tiling has remainders) and the persistent
-// tile kernel.  src is in the row-pair layout (pitch pair_pitch(W), 16-byte aligned base); dst is in the
-// row-pair layout (dst_pair) or the caller's standard layout.
+// One propagation step src -> dst: the persistent tile kernel (which also takes the column strip and, when its
+// last wave has room, the row strip) and otherwise a small row-strip launch.  src is in the row-pair layout
+// (pitch pair_pitch(W), 16-byte aligned base); dst is in the row-pair layout (dst_pair) or the caller's standard layout.
 int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, float* dst, int dst_pitch,
-                           bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s,
-                           SideLane* lane) {
+                           bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s) {
     int sm_count = 0;
     int rc = device_sm_count(dev, &sm_count);
     if (rc != PAMR_OK) return rc;
-    if (((uintptr_t)src & 15) != 0)
-        return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: source base not 16-byte aligned");
-    const int Wt = tiling.Wt, Ht = tiling.Ht, sp = pair_pitch(W);
+    if (((uintptr_t)src & 15) != 0 || ((uintptr_t)aff_tiled & 15) != 0)
+        return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: source / affinity base not 16-byte aligned");
+    const int sp = pair_pitch(W);
     if (tiling.R == 8)
-        return launch_one<8>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, Wt, Ht, cls_max, sm_count, dev, s, lane);
+        return launch_one<8>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, cls_max, sm_count, dev, s);
     if (tiling.R == 10)
-        return launch_one<10>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, Wt, Ht, cls_max, sm_count, dev, s, lane);
+        return launch_one<10>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, cls_max, sm_count, dev, s);
     return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: unsupported tiling R=%d", tiling.R);
 }
 

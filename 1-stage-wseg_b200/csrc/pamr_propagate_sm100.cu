@@ -58,7 +58,10 @@ constexpr int WIN_W = TX + 2 * HALO;  // 80 columns
 constexpr int WIN_P = WIN_W + PAMR_WIN_PAD;
 constexpr int ROWP = WIN_P * 2;       // floats per row PAIR of the window in shared memory
 constexpr int NW = 4;                 // warps per compute group (= TMEM lane quarters)
-constexpr int NG = 3;                 // compute groups that share the tile's weights in TMEM (class c -> group c % NG)
+#ifndef PAMR_NG
+#define PAMR_NG 3
+#endif
+constexpr int NG = PAMR_NG;           // compute groups that share the tile's weights in TMEM (class c -> group c % NG)
 constexpr int NWC = NG * NW;          // compute warps
 #ifndef PAMR_NSLOT
 #define PAMR_NSLOT 4
@@ -761,7 +764,8 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                     // other CTA (the concurrent column strip) could share the SM
                     if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(NW * 32) : "memory");
                     else if (grp == 1) asm volatile("bar.sync 3, %0;" ::"n"(NW * 32) : "memory");
-                    else asm volatile("bar.sync 4, %0;" ::"n"(NW * 32) : "memory");
+                    else if (grp == 2) asm volatile("bar.sync 4, %0;" ::"n"(NW * 32) : "memory");
+                    else asm volatile("bar.sync 5, %0;" ::"n"(NW * 32) : "memory");
                 }
                 const float* sp = slot + ((wq * R + HALO) / 2) * ROWP + (lane + HALO) * 2;
                 float acc[R];

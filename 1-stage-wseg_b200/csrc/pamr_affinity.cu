@@ -24,13 +24,6 @@ namespace {
 constexpr int AFF_BX = 32;
 constexpr int AFF_BY = 4;
 
-// x / y for y in the normal range, given r = rn(1/y): q = rn(x*r) corrected by the exact residual.
-__device__ __forceinline__ float div_markstein(float x, float y, float r) {
-    const float q = __fmul_rn(x, r);
-    const float e = __fmaf_rn(-q, y, x);
-    return __fmaf_rn(e, r, q);
-}
-
 // ND > 0: number of dilations known at compile time (arrays stay in registers).
 // ND == 0: runtime nd <= PAMR_MAX_DILATIONS (arrays in local memory; generic fallback).
 // TILED: write the tile-major layout (requires ND == 6); the grid then covers whole tiles and

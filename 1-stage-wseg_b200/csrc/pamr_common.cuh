@@ -179,6 +179,26 @@ __host__ __device__ __forceinline__ float scale_of(int in_size, int out_size) {
 }
 #endif
 
+#ifdef __CUDACC__
+// x / y for y in the normal range, given r = rn(1/y): q = rn(x*r) corrected by the exact residual (Markstein);
+// returns the IEEE quotient for the operand ranges of the affinity at a third of the cost of the division routine.
+__device__ __forceinline__ float div_markstein(float x, float y, float r) {
+    const float q = __fmul_rn(x, r);
+    const float e = __fmaf_rn(-q, y, x);
+    return __fmaf_rn(e, r, q);
+}
+#endif
+
+// pamr_resident.cu: affinity + all iterations in one launch for small maps (stage_net's real call shapes)
+struct ResidentPlan {
+    bool ok;                // the resident kernel applies to this problem
+    int images_per_launch;  // images whose row blocks are co-resident in one launch
+    size_t scratch_bytes;   // ping-pong buffers + barrier counters
+};
+ResidentPlan resident_plan(int B, int C, int H, int W, const Dilations& dil, int iters, int dev);
+int launch_resident(const float* img, int K, const float* m_in, float* m_out, void* scratch, size_t scratch_bytes, int B,
+                    int C, int H, int W, const Dilations& dil, int iters, unsigned* cls_max, int dev, cudaStream_t s);
+
 // Kernel launchers implemented in the .cu files (all enqueue on `s`, return a PAMR_* code).
 int launch_resize_bilinear(const float* src, float* dst, int n_planes, int h, int w, int H, int W, cudaStream_t s);
 int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, const Dilations& dil,

@@ -118,6 +118,13 @@ ScratchPlan plan_scratch(int B, int C, int H, int W, const Dilations& dil, int i
         p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * H * W, 256);
     }
     p.total = 2 * p.pingpong_each + p.aff_tiled;
+    // small maps: the resident kernel (pamr_resident.cu) carves its own ping-pong buffers + barrier counters out of
+    // the same scratch
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        const ResidentPlan rp = resident_plan(B, C, H, W, dil, iters, dev);
+        if (rp.ok && rp.scratch_bytes > p.total) p.total = rp.scratch_bytes;
+    }
     return p;
 }
 
@@ -188,6 +195,9 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
                               const float* m_in, float* m_out, void* scratch, size_t scratch_bytes, int B, int C, int H,
                               int W, const Dilations& dil, int iters, unsigned* cls_max, int dev, cudaStream_t s) {
     const size_t N = (size_t)B * C * H * W;
+    // small maps with the affinity computed here: one launch does everything (the affinity stays in registers)
+    if (img != nullptr && iters >= 1 && resident_plan(B, C, H, W, dil, iters, dev).ok)
+        return launch_resident(img, K, m_in, m_out, scratch, scratch_bytes, B, C, H, W, dil, iters, cls_max, dev, s);
     const AffTiling tiling = tuned_tiling(B, H, W, dil);
     const bool tuned = tiling.R > 0;
     if (cls_max != nullptr) {

@@ -36,7 +36,8 @@ constexpr int RS_NT = RS_NTC + 32;           // + the producer warp = 768 thread
 constexpr int RS_GRP_STRIDE = 256;           // GRP = 3: group g = threads [256 g, 256 g + 224) (the same TMEM lane quarters in every group)
 constexpr int RS_GRP_PIXELS = 224;           // blocks of at most this many pixels run 3 thread groups (one plane of a pass each)
 constexpr int RS_SMEM_MAX = 227 * 1024;
-constexpr int RS_CTRL_BYTES = 256;           // mbarriers + TMEM base address behind the stages
+constexpr int RS_CTRL_BYTES = 256;           // mbarriers and the TMEM base address behind the stages
+constexpr int RS_MAX_SEG = 4;                // class segments per iteration, each with its own per-image barrier
 constexpr int RS_MAX_STAGES = 6;
 
 __host__ __device__ constexpr int rs_dil(int id) { return id == 0 ? 1 : id == 1 ? 2 : id == 2 ? 4 : id == 3 ? 8 : id == 4 ? 12 : 24; }
@@ -58,8 +59,8 @@ struct RsGeom {
     static_assert(SLOT % 32 == 0, "slots are 128-byte aligned (bulk-copy destinations)");
     static_assert(NST >= 2 && NST <= RS_MAX_STAGES && SMEM_BYTES <= RS_SMEM_MAX, "shared memory");
 };
-using RsGeomS = RsGeom<3072, 6>;   // windows of <= 3064 floats (41 x 41 and smaller): 6 stages, 216 KB
-using RsGeomM = RsGeom<4704, 4>;   // <= 4696 floats (81 x 81 in blocks of 9 rows: 57 x 81 = 4617): 4 stages, 220.5 KB
+using RsGeomS = RsGeom<3072, 6>;   // windows of <= 3064 floats (41 x 41 and smaller): 6 stages, 217 KB
+using RsGeomM = RsGeom<4704, 4>;   // <= 4696 floats (81 x 81 in blocks of 9 rows: 57 x 81 = 4617): 4 stages, 221.75 KB
 using RsGeomL = RsGeom<9216, 2>;   // <= 9208 floats: 2 stages, 216 KB
 
 struct ResidentParams {
@@ -68,7 +69,7 @@ struct ResidentParams {
     float* m_out;        // [B,C,H,W]
     float* pp[2];        // ping-pong buffers [B,C,HWp], HWp = H*W rounded up to 4 floats (16-byte aligned planes)
     unsigned* cls_max;   // [B,C] ordered-uint maxima (zeroed by the caller) or nullptr
-    unsigned* counters;  // [B] barrier counters (zeroed by the caller)
+    unsigned* counters;  // [B][RS_MAX_SEG + 1] barrier counters: one per class segment and one for the pre-pass (zeroed by the caller)
     int K, C, H, W, iters;
     int rows_per;        // rows per CTA
     int b0;              // first image of this launch
@@ -128,24 +129,25 @@ __device__ __forceinline__ void rs_tc_fence_after() { asm volatile("tcgen05.fenc
 struct RsCtrl {  // behind the stages
     unsigned long long full[RS_MAX_STAGES];   // the stage's planes have landed (bulk copies, bytes counted)
     unsigned long long empty[RS_MAX_STAGES];  // every computing warp has read the stage
-    unsigned long long done;                  // every computing warp has stored its results of the iteration
+    unsigned long long done[RS_MAX_SEG];      // every computing warp has stored its results of the iteration's class segment
     uint32_t tmem_base;
 };
 static_assert(sizeof(RsCtrl) <= RS_CTRL_BYTES, "control block");
 
-// GRP = 1: a thread owns a pixel and takes the 3 class planes of a pass (blocks of up to 768 pixels);
-// GRP = 3: three groups of 224 threads own the same (at most 224) pixels and take one plane of the pass each, so that
-//          small blocks still put enough warps on the shared-memory pipe (one warp sustains ~1 LDS per 16 cycles).
+// A thread owns a pixel and takes the 3 class planes of a pass.
+// GRP = 1: blocks of up to 736 pixels, every warp works on every pass;
+// GRP = 3: three groups of 224 threads own the same (at most 224) pixels and take every third pass of the sequence
+//          each, so that small blocks still put 21 warps on the shared-memory pipe.
 // Warp 23 is the producer: per-image barrier between iterations and the bulk copies of the class-plane windows.
 template <int GRP, class GEO>
 __global__ void __launch_bounds__(RS_NT, 1)
 pamr_resident_kernel(const ResidentParams prm) {
-    constexpr int PPT = RS_CPP / GRP;  // planes per thread and pass
+    constexpr int PPT = RS_CPP;  // planes per thread and pass
     constexpr int NST = GEO::NST;
     extern __shared__ __align__(128) float rs_smem[];
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(rs_smem);
     RsCtrl* ctrl = reinterpret_cast<RsCtrl*>(reinterpret_cast<unsigned char*>(rs_smem) + GEO::CTRL_OFF);
-    const uint32_t full0 = sbase + GEO::CTRL_OFF, empty0 = full0 + 8 * RS_MAX_STAGES, done_bar = empty0 + 8 * RS_MAX_STAGES;
+    const uint32_t full0 = sbase + GEO::CTRL_OFF, empty0 = full0 + 8 * RS_MAX_STAGES, done0 = empty0 + 8 * RS_MAX_STAGES;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const bool producer = warp == RS_NWC;
     const int grp = (GRP == 1 || producer) ? 0 : t / RS_GRP_STRIDE, tl = (GRP == 1) ? t : t % RS_GRP_STRIDE;
@@ -159,14 +161,21 @@ pamr_resident_kernel(const ResidentParams prm) {
     // bulk copies move the 16-byte aligned range [s0, e1) of a plane; the window starts m0 floats into it
     const int s0 = (wy0 * W) & ~3, m0 = wy0 * W - s0;
     const uint32_t copy_bytes = (uint32_t)((min((wy1 * W + 3) & ~3, (int)HWp) - s0) * 4);
-    const int nwarps_c = GRP * ((nown + 31) / 32);  // warps that compute
+    const int nwarps_g = (nown + 31) / 32;  // warps of a group that compute
 
+    const int npass = (C + RS_CPP - 1) / RS_CPP;
+    // class segments: passes [seg_lo(s), seg_lo(s+1)).  With spare warps (GRP = 3) a separate signaller warp does the
+    // arrivals and 4 segments fit; otherwise the producer does both jobs and 2 segments is what it can keep up with
+    const int nseg = min(npass, GRP == 3 ? RS_MAX_SEG : 2);
+    auto seg_lo = [&](int sg) { return sg * npass / nseg; };
     if (t == 0) {
         for (int i = 0; i < NST; ++i) {
             rs_mbar_init(full0 + 8 * i, 1);
-            rs_mbar_init(empty0 + 8 * i, nwarps_c);
+            rs_mbar_init(empty0 + 8 * i, nwarps_g);  // a stage is read by the warps of one group
         }
-        rs_mbar_init(done_bar, nwarps_c);
+        // GRP = 1: a warp arrives once per segment it has stored.  GRP = 3: once per pass it has stored, so that segment
+        // sg is done after (its passes) x (warps of a group) arrivals
+        for (int i = 0; i < nseg; ++i) rs_mbar_init(done0 + 8 * i, GRP == 1 ? nwarps_g : nwarps_g * (seg_lo(i + 1) - seg_lo(i)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {  // Tensor Memory: the pixels' 48 weights live there, one TMEM lane per thread (see below)
@@ -201,27 +210,23 @@ pamr_resident_kernel(const ResidentParams prm) {
     {
         const float* __restrict__ mi = prm.m_in + (size_t)b * C * HW + (size_t)y0 * W;
         float* __restrict__ mo = prm.pp[1] + (size_t)b * C * HWp + (size_t)y0 * W;
-        const int n = nown * C;  // (plane, pixel) pairs
-        for (int i0 = t; i0 < n; i0 += RS_NT * 8) {
+        // nown <= RS_NTC < RS_NT: one pixel per thread and plane, 8 planes in flight
+        for (int c0 = 0; c0 < C; c0 += 8) {
             float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * RS_NT;
-                if (i < n) { const int c = i / nown, e = i - c * nown; v[u] = __ldg(mi + (size_t)c * HW + e); }
-            }
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u < C && t < nown) v[u] = __ldg(mi + (size_t)(c0 + u) * HW + t);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * RS_NT;
-                if (i < n) { const int c = i / nown, e = i - c * nown; mo[(size_t)c * HWp + e] = v[u]; }
-            }
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u < C && t < nown) mo[(size_t)(c0 + u) * HWp + t] = v[u];
         }
     }
-    unsigned* ctr = prm.counters + b;
+    unsigned* ctr = prm.counters + (size_t)(RS_MAX_SEG + 1) * b;  // [s < RS_MAX_SEG]: segment s stored; [RS_MAX_SEG]: pre-pass stored
     const unsigned G = gridDim.x;
     rs_tc_fence_before();
     __syncthreads();  // the mask rows are stored; mbarrier init and the TMEM base address are published
     rs_tc_fence_after();
-    if (t == RS_NTC) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");  // pre-pass done (arrival 1 of this CTA)
+    if (t == RS_NTC) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr + RS_MAX_SEG) : "memory");  // pre-pass stored
 
     // ================= affinity (pamr.py:132-136) =================
     // TMEM layout.  A warp reaches the 32 lanes of quarter warp % 4; thread <-> lane.  Threads that share a quarter
@@ -233,6 +238,9 @@ pamr_resident_kernel(const ResidentParams prm) {
     const uint32_t t_w = tq + (GRP == 1 ? 0u : 3u * 96u);  // where the passes read the weights
     const bool split = (GRP > 1) && prm.K <= GRP;          // group g computes image channel g alone
     constexpr int IMG_ST = NST - 1;                         // the image planes borrow the last stage
+#if defined(PAMR_EXPERIMENTS) && defined(RS_X_STOP)        // timing ablation: 1 = stop after the pre-pass, 2 = after the affinity, 3 = affinity without softmax
+    if (RS_X_STOP != 1)
+#endif
     {
         for (int k0 = 0; k0 < prm.K; k0 += RS_CPP) {
             const int nk = min(RS_CPP, prm.K - k0);
@@ -252,6 +260,9 @@ pamr_resident_kernel(const ResidentParams prm) {
             for (int kk = 0; kk < nk; ++kk) {
                 // who computes channel k0 + kk: its group when the channels are split, else group 0
                 if (!wactive || grp != (split ? kk : 0)) continue;
+                // (keeps ptxas from hoisting the 48 tap addresses rb + co out of this loop -- into spill slots)
+#pragma unroll
+                for (int i = 0; i < 12; ++i) asm volatile("" : "+r"(co[i]));
                 const uint32_t po = (uint32_t)(IMG_ST * GEO::STAGE_BYTES) + (uint32_t)(kk * GEO::SLOT) * 4u;
 #define RS_SMP(i, j) lds_f32(RS_ADDR(i, (j) / 3 - 1, (j) % 3 - 1) + po)
                 // unbiased std of the 54 samples in fp32, centre-shifted, 6 partial sums (see pamr_affinity.cu)
@@ -309,6 +320,9 @@ pamr_resident_kernel(const ResidentParams prm) {
             __syncthreads();
             rs_tc_fence_after();
         }
+#if defined(PAMR_EXPERIMENTS) && defined(RS_X_STOP)
+        if (RS_X_STOP != 3)
+#endif
         if (wactive && grp == 0) {
             // mean over the channels, softmax over the 48 taps (summed in the reference's tap order p, like every other path)
             asm volatile("" : "+r"(x), "+r"(y));  // rb / co are rebuilt afterwards: their 25 registers are free meanwhile
@@ -361,104 +375,129 @@ pamr_resident_kernel(const ResidentParams prm) {
         rs_tc_fence_after();
         neighbour_addresses();
     }
-    if (GRP > 1) {  // group g reads plane g of every pass
-#pragma unroll
-        for (int i = 0; i < 13; ++i) rb[i] += (uint32_t)(grp * PPT * GEO::SLOT) * 4u;
-    }
-
     // ================= propagation (pamr.py:138-140) =================
     // Passes form one sequence n = it * npass + p over all iterations: stage n % NST, barrier phase (n / NST) & 1.
-    const int npass = (C + RS_CPP - 1) / RS_CPP;
-    if (producer) {
+    // Class planes propagate independently: segment s of iteration it+1 needs only segment s of iteration it from the
+    // other CTAs of the image.  So every segment has its own per-image barrier (a counter in global memory), and the
+    // round trip store -> release -> acquire -> bulk copy from L2 (~2 us) hides behind the passes of the other segments.
+    const bool signaller = (GRP == 3) && warp == 7;  // (an idle warp of group 0: its 32 pixel slots are beyond RS_GRP_PIXELS)
+#if defined(PAMR_EXPERIMENTS) && defined(RS_X_STOP)
+    if (false) {
+    } else if (false)
+#endif
+    if (signaller) {
+        // arrivals: once every computing warp of this CTA has stored segment sg of iteration it, tell the image
+        if (lane == 0) {
+            for (int it = 0; it + 1 < prm.iters; ++it)
+                for (int sg = 0; sg < nseg; ++sg) {
+                    rs_mbar_wait(done0 + 8 * sg, (uint32_t)it & 1u);
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr + sg) : "memory");
+                }
+        }
+    } else if (producer) {
         if (lane == 0) {
             int n = 0;
             for (int it = 0; it < prm.iters; ++it) {
-                // ---- per-image barrier: every CTA of the image has stored its rows of the previous iteration (it = 0: pre-pass)
-                if (it > 0) {
-                    rs_mbar_wait(done_bar, (uint32_t)(it - 1) & 1u);  // this CTA's warps have stored theirs
-                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-                }
-#if !(defined(PAMR_EXPERIMENTS) && defined(RS_X_NOBARRIER))
-                {
-                    const unsigned target = G * (unsigned)(it + 1);
-                    unsigned seen, spins = 0;
-                    do {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-                        if (seen < target && ++spins > (1u << 22)) __trap();
-                    } while (seen < target);
-                }
-#endif
-                __threadfence();
-                asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies (async proxy) come after the other CTAs' stores
                 const float* src = prm.pp[(it + 1) & 1] + (size_t)b * C * HWp + s0;
-                for (int p = 0; p < npass; ++p, ++n) {
-                    const int st = n % NST;
-                    if (n >= NST) rs_mbar_wait(empty0 + 8 * st, (uint32_t)(n / NST - 1) & 1u);  // the stage's previous planes are consumed
-                    const int np = min(RS_CPP, C - p * RS_CPP);
-                    const uint32_t bar = full0 + 8 * st;
-                    rs_mbar_expect_tx(bar, copy_bytes * (uint32_t)np);
-                    for (int j = 0; j < np; ++j)
-                        rs_bulk_load(sbase + (uint32_t)(st * GEO::STAGE_BYTES) + (uint32_t)(j * GEO::SLOT) * 4u,
-                                     src + (size_t)(p * RS_CPP + j) * HWp, copy_bytes, bar);
+                for (int sg = 0; sg < nseg; ++sg) {
+                    if (GRP != 3 && it > 0) {  // no signaller warp: this thread does the arrival as well
+                        rs_mbar_wait(done0 + 8 * sg, (uint32_t)(it - 1) & 1u);
+                        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr + sg) : "memory");
+                    }
+#if !(defined(PAMR_EXPERIMENTS) && defined(RS_X_NOBARRIER))
+                    if (it > 0 || sg == 0) {  // every CTA of the image has stored segment sg of the previous iteration (it = 0: the pre-pass)
+                        const unsigned* c_ = ctr + (it == 0 ? RS_MAX_SEG : sg);
+                        const unsigned target = G * (unsigned)(it == 0 ? 1 : it);
+                        unsigned seen, spins = 0;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(c_) : "memory");
+                            if (seen < target && ++spins > (1u << 22)) __trap();
+                        } while (seen < target);
+                        asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies (async proxy) come after the other CTAs' stores
+                    }
+#endif
+                    for (int p = seg_lo(sg); p < seg_lo(sg + 1); ++p, ++n) {
+                        const int st = n % NST;
+                        if (n >= NST) rs_mbar_wait(empty0 + 8 * st, (uint32_t)(n / NST - 1) & 1u);  // the stage's previous planes are consumed
+                        const int np = min(RS_CPP, C - p * RS_CPP);
+                        const uint32_t bar = full0 + 8 * st;
+                        rs_mbar_expect_tx(bar, copy_bytes * (uint32_t)np);
+                        for (int j = 0; j < np; ++j)
+                            rs_bulk_load(sbase + (uint32_t)(st * GEO::STAGE_BYTES) + (uint32_t)(j * GEO::SLOT) * 4u,
+                                         src + (size_t)(p * RS_CPP + j) * HWp, copy_bytes, bar);
+                    }
                 }
             }
         }
     } else if (wactive) {
-        int n = 0;
-        for (int it = 0; it < prm.iters; ++it) {
+        const int total = prm.iters * npass;
+        int it = 0, p = grp, sg = 0, st = grp % NST;  // pass n = (it, p), its segment and its stage
+        uint32_t ph = (uint32_t)(grp / NST) & 1u;       // (n / NST) & 1
+        while (p >= npass) { p -= npass; ++it; }
+        float* obase = (it >= prm.iters - 1 ? prm.m_out + (size_t)b * C * HW : prm.pp[it & 1] + (size_t)b * C * HWp) + (size_t)y0 * W + tl;
+        for (int n = grp; n < total; n += GRP) {  // group g takes passes n = g (mod GRP) of the sequence
             const bool last_it = (it == prm.iters - 1);
-            float* __restrict__ dst = (last_it ? prm.m_out + (size_t)b * C * HW : prm.pp[it & 1] + (size_t)b * C * HWp) + (size_t)y0 * W + tl;
             const size_t dps = last_it ? HW : HWp;
-            for (int p = 0; p < npass; ++p, ++n) {
-                const int st = n % NST;
-                const uint32_t sto = (uint32_t)(st * GEO::STAGE_BYTES);
-                rs_mbar_wait(full0 + 8 * st, (uint32_t)(n / NST) & 1u);
-                float acc[PPT];
+            const uint32_t sto = (uint32_t)(st * GEO::STAGE_BYTES);
+            rs_mbar_wait(full0 + 8 * st, ph);
+            float acc[PPT];
 #pragma unroll
-                for (int j = 0; j < PPT; ++j) acc[j] = 0.f;
+            for (int j = 0; j < PPT; ++j) acc[j] = 0.f;
 #if !(defined(PAMR_EXPERIMENTS) && defined(RS_X_NOCOMPUTE))
-                float wb[2][8];  // the weights stream out of TMEM in six 8-tap batches, double buffered
-                rs_tmem_ld8(t_w, wb[0]);
+            float wb[2][8];  // the weights stream out of TMEM in six 8-tap batches, double buffered
+            rs_tmem_ld8(t_w, wb[0]);
 #pragma unroll
-                for (int bt = 0; bt < 6; ++bt) {
-                    float v[8][PPT];  // the batch's neighbours: all loads in flight before the first FMA
+            for (int bt = 0; bt < 6; ++bt) {
+                float v[8][PPT];  // the batch's neighbours: all loads in flight before the first FMA
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int pt = seq_tap(bt * 8 + i), id = pt >> 3, j8 = pt & 7;
-                        const uint32_t ad = RS_ADDR(id, rs_ty(j8), rs_tx(j8)) + sto;
+                for (int i = 0; i < 8; ++i) {
+                    const int pt = seq_tap(bt * 8 + i), id = pt >> 3, j8 = pt & 7;
+                    const uint32_t ad = RS_ADDR(id, rs_ty(j8), rs_tx(j8)) + sto;
 #pragma unroll
-                        for (int j = 0; j < PPT; ++j) v[i][j] = lds_f32(ad + (uint32_t)(j * GEO::SLOT) * 4u);
-                    }
-                    rs_tmem_wait_ld8(wb[bt & 1]);
-                    if (bt + 1 < 6) rs_tmem_ld8(t_w + (bt + 1) * 8, wb[(bt + 1) & 1]);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-#pragma unroll
-                        for (int j = 0; j < PPT; ++j) acc[j] = fmaf(wb[bt & 1][i], v[i][j], acc[j]);
-                    }
+                    for (int j = 0; j < PPT; ++j) v[i][j] = lds_f32(ad + (uint32_t)(j * GEO::SLOT) * 4u);
                 }
-#endif
-                __syncwarp();
-                if (lane == 0) rs_mbar_arrive(empty0 + 8 * st);  // this warp is done with the stage
-                const int c0 = p * RS_CPP + grp * PPT;
-                float* __restrict__ o = dst + (size_t)c0 * dps;
-                if (active) {
+                rs_tmem_wait_ld8(wb[bt & 1]);
+                if (bt + 1 < 6) rs_tmem_ld8(t_w + (bt + 1) * 8, wb[(bt + 1) & 1]);
 #pragma unroll
-                    for (int j = 0; j < PPT; ++j)
-                        if (c0 + j < C) o[(size_t)j * dps] = acc[j];
-                }
-                if (last_it && prm.cls_max != nullptr) {
-                    unsigned* cm = prm.cls_max + (size_t)b * C + c0;
+                for (int i = 0; i < 8; ++i) {
 #pragma unroll
-                    for (int j = 0; j < PPT; ++j) {
-                        const unsigned m = __reduce_max_sync(0xffffffffu, active ? ordered_from_float(acc[j]) : 0u);
-                        if (lane == 0 && c0 + j < C && m != 0u) atomicMax(cm + j, m);
-                    }
+                    for (int j = 0; j < PPT; ++j) acc[j] = fmaf(wb[bt & 1][i], v[i][j], acc[j]);
                 }
             }
-            if (!last_it) {  // this warp's rows of the iteration are stored
-                __syncwarp();
-                if (lane == 0) rs_mbar_arrive(done_bar);
+#endif
+            __syncwarp();
+            if (lane == 0) rs_mbar_arrive(empty0 + 8 * st);  // this warp is done with the stage
+            const int c0 = p * RS_CPP;
+            float* __restrict__ o = obase + (size_t)c0 * dps;
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < PPT; ++j)
+                    if (c0 + j < C) o[(size_t)j * dps] = acc[j];
+            }
+            if (last_it && prm.cls_max != nullptr) {
+                unsigned* cm = prm.cls_max + (size_t)b * C + c0;
+#pragma unroll
+                for (int j = 0; j < PPT; ++j) {
+                    const unsigned m = __reduce_max_sync(0xffffffffu, active ? ordered_from_float(acc[j]) : 0u);
+                    if (lane == 0 && c0 + j < C && m != 0u) atomicMax(cm + j, m);
+                }
+            }
+            if (!last_it) {  // this warp's rows of the pass are stored
+                while (p >= seg_lo(sg + 1)) ++sg;
+                if (GRP > 1 || p + 1 == seg_lo(sg + 1)) {
+                    __syncwarp();
+                    if (lane == 0) rs_mbar_arrive(done0 + 8 * sg);
+                }
+            }
+            // next pass of this group
+            st += GRP % NST;
+            if (st >= NST) { st -= NST; ph ^= 1u; }
+            if (GRP >= NST && (GRP / NST) % 2) ph ^= 1u;
+            p += GRP;
+            if (p >= npass) {
+                do { p -= npass; ++it; } while (p >= npass);
+                sg = 0;
+                obase = (it == prm.iters - 1 ? prm.m_out + (size_t)b * C * HW : prm.pp[it & 1] + (size_t)b * C * HWp) + (size_t)y0 * W + tl;
             }
         }
     }
@@ -534,7 +573,7 @@ ResidentPlan resident_plan(int B, int C, int H, int W, const Dilations& dil, int
     r.ok = true;
     r.images_per_launch = sms / g_min;
     if (r.images_per_launch > 65535) r.images_per_launch = 65535;
-    r.scratch_bytes = 2 * rs_align(sizeof(float) * (size_t)B * C * rs_plane_stride(H, W), 256) + rs_align(sizeof(unsigned) * (size_t)B, 256);
+    r.scratch_bytes = 2 * rs_align(sizeof(float) * (size_t)B * C * rs_plane_stride(H, W), 256) + rs_align(sizeof(unsigned) * (size_t)B * (RS_MAX_SEG + 1), 256);
     return r;
 }
 
@@ -554,8 +593,8 @@ int launch_resident(const float* img, int K, const float* m_in, float* m_out, vo
     p.cls_max = cls_max;
     p.K = K; p.C = C; p.H = H; p.W = W; p.iters = iters;
     {
-        const size_t nmax = cls_max != nullptr ? (size_t)B * C : 0, n = nmax + (size_t)B;
-        rs_zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cls_max, nmax, p.counters, (size_t)B);
+        const size_t nmax = cls_max != nullptr ? (size_t)B * C : 0, nctr = (size_t)B * (RS_MAX_SEG + 1), n = nmax + nctr;
+        rs_zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cls_max, nmax, p.counters, nctr);
         count_launch();
         PAMR_CUDA_TRY(cudaGetLastError());
     }

@@ -199,6 +199,12 @@ ResidentPlan resident_plan(int B, int C, int H, int W, const Dilations& dil, int
 int launch_resident(const float* img, int K, const float* m_in, float* m_out, void* scratch, size_t scratch_bytes, int B,
                     int C, int H, int W, const Dilations& dil, int iters, unsigned* cls_max, int dev, cudaStream_t s);
 
+// pamr_propagate_sm100.cu: 1-D TMA descriptor over a flat fp32 array (map points at a CUtensorMap)
+int encode_tensor_map_1d_f32(void* map, const float* base, unsigned long long elems, unsigned box);
+int device_sm_count(int dev, int* out);
+// pamr_affinity.cu: LocalStDev (pamr.py:77-103) on its own, img [B,K,H,W] -> sd [B,K,H,W]
+int launch_local_std(const float* img, float* sd, int B, int K, int H, int W, const Dilations& dil, cudaStream_t s);
+
 // Kernel launchers implemented in the .cu files (all enqueue on `s`, return a PAMR_* code).
 int launch_resize_bilinear(const float* src, float* dst, int n_planes, int h, int w, int H, int W, cudaStream_t s);
 int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, const Dilations& dil,

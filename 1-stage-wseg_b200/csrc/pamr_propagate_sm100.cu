@@ -973,6 +973,22 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
 
 }  // namespace
 
+// 1-D map over a flat fp32 array (pamr_affinity.cu: image rows are fetched one box of `box` floats at a time, at any
+// 4-byte offset -- W needs no alignment; only the base must be 16-byte aligned).  `map` points at a CUtensorMap.
+int encode_tensor_map_1d_f32(void* map, const float* base, unsigned long long elems, unsigned box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return set_error(PAMR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[1] = {(cuuint64_t)elems};
+    cuuint64_t strides[1] = {0};  // rank - 1 = 0 entries are read
+    cuuint32_t bx[1] = {(cuuint32_t)box};
+    cuuint32_t estr[1] = {1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, const_cast<float*>(base), dims,
+                    strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(PAMR_ERR_CUDA, "cuTensorMapEncodeTiled (1-D) failed with CUresult %d", (int)r);
+    return PAMR_OK;
+}
+
 #ifdef PAMR_EXPERIMENTS
 // Debug hook of experiment builds only (not part of the ABI): device buffer of 5 x 4096 x 2 int64 that CTA `cta`
 // of ONE tuned launch (after skipping `skip` launches) fills with {clock64, event code} pairs.

@@ -39,6 +39,13 @@ constexpr int RS_SMEM_MAX = 227 * 1024;
 constexpr int RS_CTRL_BYTES = 256;           // mbarriers and the TMEM base address behind the stages
 constexpr int RS_MAX_SEG = 4;                // class segments per iteration, each with its own per-image barrier
 constexpr int RS_MAX_STAGES = 6;
+// mbarriers of the stage ring: pass n of the sequence uses stage n % NST but barrier pair n % RS_NBAR.  Waits are by
+// phase PARITY, which is only sound if a waiter can never be a whole phase ahead of its barrier, i.e. if pass
+// n - RS_NBAR has landed by the time a group waits for pass n.  The group has consumed pass n - GRP, and the producer
+// issued that one only after pass n - GRP - NST had been consumed; so RS_NBAR >= GRP + NST is sufficient for any
+// combination of groups and stages (with one barrier per stage, 3 groups on 2 stages alias at once, and 3 groups on
+// 4 stages alias whenever two bulk copies complete out of order).
+constexpr int RS_NBAR = 12;
 
 __host__ __device__ constexpr int rs_dil(int id) { return id == 0 ? 1 : id == 1 ? 2 : id == 2 ? 4 : id == 3 ? 8 : id == 4 ? 12 : 24; }
 // tap j of the 3x3 neighbourhood without the centre (pamr.py:25-34)
@@ -127,12 +134,13 @@ __device__ __forceinline__ void rs_tc_fence_before() { asm volatile("tcgen05.fen
 __device__ __forceinline__ void rs_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 struct RsCtrl {  // behind the stages
-    unsigned long long full[RS_MAX_STAGES];   // the stage's planes have landed (bulk copies, bytes counted)
-    unsigned long long empty[RS_MAX_STAGES];  // every computing warp has read the stage
+    unsigned long long full[RS_NBAR];         // the pass's planes have landed in its stage (bulk copies, bytes counted)
+    unsigned long long empty[RS_NBAR];        // every computing warp has read them
     unsigned long long done[RS_MAX_SEG];      // every computing warp has stored its results of the iteration's class segment
     uint32_t tmem_base;
 };
 static_assert(sizeof(RsCtrl) <= RS_CTRL_BYTES, "control block");
+static_assert(RS_NBAR >= 3 + RS_MAX_STAGES, "barrier ring: groups + stages");
 
 // A thread owns a pixel and takes the 3 class planes of a pass.
 // GRP = 1: blocks of up to 736 pixels, every warp works on every pass;
@@ -147,7 +155,7 @@ pamr_resident_kernel(const ResidentParams prm) {
     extern __shared__ __align__(128) float rs_smem[];
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(rs_smem);
     RsCtrl* ctrl = reinterpret_cast<RsCtrl*>(reinterpret_cast<unsigned char*>(rs_smem) + GEO::CTRL_OFF);
-    const uint32_t full0 = sbase + GEO::CTRL_OFF, empty0 = full0 + 8 * RS_MAX_STAGES, done0 = empty0 + 8 * RS_MAX_STAGES;
+    const uint32_t full0 = sbase + GEO::CTRL_OFF, empty0 = full0 + 8 * RS_NBAR, done0 = empty0 + 8 * RS_NBAR;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const bool producer = warp == RS_NWC;
     const int grp = (GRP == 1 || producer) ? 0 : t / RS_GRP_STRIDE, tl = (GRP == 1) ? t : t % RS_GRP_STRIDE;
@@ -169,9 +177,9 @@ pamr_resident_kernel(const ResidentParams prm) {
     const int nseg = min(npass, GRP == 3 ? RS_MAX_SEG : 2);
     auto seg_lo = [&](int sg) { return sg * npass / nseg; };
     if (t == 0) {
-        for (int i = 0; i < NST; ++i) {
+        for (int i = 0; i < RS_NBAR; ++i) {
             rs_mbar_init(full0 + 8 * i, 1);
-            rs_mbar_init(empty0 + 8 * i, nwarps_g);  // a stage is read by the warps of one group
+            rs_mbar_init(empty0 + 8 * i, nwarps_g);  // a pass is read by the warps of one group
         }
         // GRP = 1: a warp arrives once per segment it has stored.  GRP = 3: once per pass it has stored, so that segment
         // sg is done after (its passes) x (warps of a group) arrivals
@@ -376,7 +384,8 @@ pamr_resident_kernel(const ResidentParams prm) {
         neighbour_addresses();
     }
     // ================= propagation (pamr.py:138-140) =================
-    // Passes form one sequence n = it * npass + p over all iterations: stage n % NST, barrier phase (n / NST) & 1.
+    // Passes form one sequence n = it * npass + p over all iterations: stage n % NST, barrier pair n % RS_NBAR, barrier
+    // phase (n / RS_NBAR) & 1.
     // Class planes propagate independently: segment s of iteration it+1 needs only segment s of iteration it from the
     // other CTAs of the image.  So every segment has its own per-image barrier (a counter in global memory), and the
     // round trip store -> release -> acquire -> bulk copy from L2 (~2 us) hides behind the passes of the other segments.
@@ -418,9 +427,12 @@ pamr_resident_kernel(const ResidentParams prm) {
 #endif
                     for (int p = seg_lo(sg); p < seg_lo(sg + 1); ++p, ++n) {
                         const int st = n % NST;
-                        if (n >= NST) rs_mbar_wait(empty0 + 8 * st, (uint32_t)(n / NST - 1) & 1u);  // the stage's previous planes are consumed
+                        if (n >= NST) {  // the stage's previous planes (pass n - NST) are consumed
+                            const int pn = n - NST;
+                            rs_mbar_wait(empty0 + 8 * (pn % RS_NBAR), (uint32_t)(pn / RS_NBAR) & 1u);
+                        }
                         const int np = min(RS_CPP, C - p * RS_CPP);
-                        const uint32_t bar = full0 + 8 * st;
+                        const uint32_t bar = full0 + 8 * (n % RS_NBAR);
                         rs_mbar_expect_tx(bar, copy_bytes * (uint32_t)np);
                         for (int j = 0; j < np; ++j)
                             rs_bulk_load(sbase + (uint32_t)(st * GEO::STAGE_BYTES) + (uint32_t)(j * GEO::SLOT) * 4u,
@@ -431,15 +443,15 @@ pamr_resident_kernel(const ResidentParams prm) {
         }
     } else if (wactive) {
         const int total = prm.iters * npass;
-        int it = 0, p = grp, sg = 0, st = grp % NST;  // pass n = (it, p), its segment and its stage
-        uint32_t ph = (uint32_t)(grp / NST) & 1u;       // (n / NST) & 1
+        int it = 0, p = grp, sg = 0, st = grp % NST, bi = grp;  // pass n = (it, p), its segment, its stage and its barrier pair
+        uint32_t ph = 0u;                                        // (n / RS_NBAR) & 1
         while (p >= npass) { p -= npass; ++it; }
         float* obase = (it >= prm.iters - 1 ? prm.m_out + (size_t)b * C * HW : prm.pp[it & 1] + (size_t)b * C * HWp) + (size_t)y0 * W + tl;
         for (int n = grp; n < total; n += GRP) {  // group g takes passes n = g (mod GRP) of the sequence
             const bool last_it = (it == prm.iters - 1);
             const size_t dps = last_it ? HW : HWp;
             const uint32_t sto = (uint32_t)(st * GEO::STAGE_BYTES);
-            rs_mbar_wait(full0 + 8 * st, ph);
+            rs_mbar_wait(full0 + 8 * bi, ph);
             float acc[PPT];
 #pragma unroll
             for (int j = 0; j < PPT; ++j) acc[j] = 0.f;
@@ -466,7 +478,7 @@ pamr_resident_kernel(const ResidentParams prm) {
             }
 #endif
             __syncwarp();
-            if (lane == 0) rs_mbar_arrive(empty0 + 8 * st);  // this warp is done with the stage
+            if (lane == 0) rs_mbar_arrive(empty0 + 8 * bi);  // this warp is done with the stage
             const int c0 = p * RS_CPP;
             float* __restrict__ o = obase + (size_t)c0 * dps;
             if (active) {
@@ -491,8 +503,9 @@ pamr_resident_kernel(const ResidentParams prm) {
             }
             // next pass of this group
             st += GRP % NST;
-            if (st >= NST) { st -= NST; ph ^= 1u; }
-            if (GRP >= NST && (GRP / NST) % 2) ph ^= 1u;
+            if (st >= NST) st -= NST;
+            bi += GRP;
+            if (bi >= RS_NBAR) { bi -= RS_NBAR; ph ^= 1u; }
             p += GRP;
             if (p >= npass) {
                 do { p -= npass; ++it; } while (p >= npass);

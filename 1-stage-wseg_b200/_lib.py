@@ -29,6 +29,7 @@ SIGNATURES = {
     "pamr_launch_count": (ctypes.c_ulonglong, []),
     "pamr_resize_bilinear_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "pamr_affinity_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "pamr_local_std_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "pamr_propagate_scratch_bytes": (ctypes.c_size_t, [_i] * 4 + [_vp, _i, _i]),
     "pamr_propagate_f32": (_i, [_vp, _vp, _vp, _vp, ctypes.c_size_t, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp]),
     "pamr_forward_workspace_bytes": (ctypes.c_size_t, [_i] * 7 + [_vp, _i, _i]),

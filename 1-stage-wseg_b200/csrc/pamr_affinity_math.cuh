@@ -8,7 +8,7 @@
 //
 // The kernels are instruction-issue bound, so the arithmetic is arranged for few instructions at (measured) no loss of
 // accuracy against the reference -- tools/affinity_numerics.py emulates every variant in fp32 on nine input families
-// (max-abs error of the 48 weights against the double-Welford / IEEE-division oracle):
+// (max-abs error of the 48 weights against the double-Welford / IEEE-division CPU restatement of the reference):
 //   fully IEEE fp32 (two-pass std, division, expf, division)             2.4e-7 .. 5.4e-7
 //   this file (two-pass std, reciprocal + FMA, ex2.approx, reciprocal)   3.0e-7 .. 5.7e-7
 //   one-pass std (sum u, sum u^2) + the same                             up to 2.2e-6   (rejected)
@@ -55,7 +55,7 @@ __device__ __forceinline__ float std_from_shifted(const float (&u)[8 * NDT], int
         for (int i = 0; i < NDT; ++i) s1 += part[i];
     }
     const float n = (float)(9 * nd);
-    const float mean_u = (NDT == 6) ? s1 * (1.0f / 54.0f) : s1 / n;
+    const float mean_u = (nd == 6) ? s1 * (1.0f / 54.0f) : s1 / n;
 #pragma unroll
     for (int i = 0; i < NDT; ++i) {
         float t = 0.f;
@@ -77,7 +77,7 @@ __device__ __forceinline__ float std_from_shifted(const float (&u)[8 * NDT], int
 #pragma unroll
         for (int i = 0; i < NDT; ++i) m2 += part[i];
     }
-    return sqrtf((NDT == 6) ? m2 * (1.0f / 53.0f) : m2 / (n - 1.0f));
+    return sqrtf((nd == 6) ? m2 * (1.0f / 53.0f) : m2 / (n - 1.0f));
 }
 
 // nr_k of the header comment from the channel's std
@@ -86,13 +86,16 @@ __device__ __forceinline__ float neg_scaled_rcp_den(float sd, float log2e_over_k
     return -(__frcp_rn(den) * log2e_over_k);
 }
 
-// Softmax of the 8*ND base-2 logits A (in place: A becomes the weights), pamr.py:136.
+// Softmax of the 8*ND base-2 logits A (in place: A becomes the weights), pamr.py:136.  `scale` multiplies every
+// weight (1, or 0 for a pixel whose weights must be zero).  Maximum and sum are formed as four interleaved partial
+// chains: the kernels run few warps per scheduler, so a 48-long dependent chain would sit on the issue slot.
 template <int NDT>
-__device__ __forceinline__ void softmax_base2(float (&A)[8 * NDT], int nd) {
-    float mx = -INFINITY;
+__device__ __forceinline__ void softmax_base2(float (&A)[8 * NDT], int nd, float scale = 1.0f) {
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
     for (int p = 0; p < 8 * NDT; ++p)
-        if (p < 8 * nd) mx = fmaxf(mx, A[p]);
+        if (p < 8 * nd) m4[p & 3] = fmaxf(m4[p & 3], A[p]);
+    const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
     float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int p = 0; p < 8 * NDT; ++p) {
@@ -101,7 +104,7 @@ __device__ __forceinline__ void softmax_base2(float (&A)[8 * NDT], int nd) {
             s[p & 3] += A[p];
         }
     }
-    const float rs = __frcp_rn((s[0] + s[1]) + (s[2] + s[3]));  // the sum is in [1, 8 nd]
+    const float rs = __frcp_rn((s[0] + s[1]) + (s[2] + s[3])) * scale;  // the sum is in [1, 8 nd]
 #pragma unroll
     for (int p = 0; p < 8 * NDT; ++p)
         if (p < 8 * nd) A[p] *= rs;
@@ -113,7 +116,7 @@ __device__ __forceinline__ void softmax_base2(float (&A)[8 * NDT], int nd) {
 // The channel loops are kept rolled (#pragma unroll 1): the unrolled body of one channel is ~400 instructions.
 constexpr int AFF_MAXK = 8;
 template <int NDT, class Fetch>
-__device__ __forceinline__ void affinity_pixel(const Fetch& fetch, int K, int nd, float (&w)[8 * NDT]) {
+__device__ __forceinline__ void affinity_pixel(const Fetch& fetch, int K, int nd, float (&w)[8 * NDT], float scale = 1.0f) {
     float nr[AFF_MAXK];  // indexed only with compile-time constants below (registers)
 #pragma unroll
     for (int k = 0; k < AFF_MAXK; ++k) nr[k] = 0.f;
@@ -152,7 +155,7 @@ __device__ __forceinline__ void affinity_pixel(const Fetch& fetch, int K, int nd
             }
         }
     }
-    softmax_base2<NDT>(w, nd);
+    softmax_base2<NDT>(w, nd, scale);
 }
 
 }  // namespace pamr

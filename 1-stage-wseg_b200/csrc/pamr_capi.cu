@@ -143,7 +143,19 @@ int pamr_affinity_f32(const float* img, float* aff, int B, int K, int H, int W, 
     PAMR_TRY(check_dims(B, K, H, W));
     Dilations dil;
     PAMR_TRY(make_dilations(dilations, nd, &dil));
-    return launch_affinity(img, aff, B, K, H, W, dil, AffTiling{}, (cudaStream_t)stream);
+    return launch_affinity(img, aff, B, K, H, W, dil, AffTiling{}, nullptr, (cudaStream_t)stream);
+}
+
+int pamr_local_std_f32(const float* img, float* sd, int B, int K, int H, int W, const int* dilations, int nd, int dev,
+                       pamr_stream_t stream) {
+    PAMR_ENTER(dev);
+    PAMR_REQUIRE(img && sd, "local_std: NULL pointer");
+    PAMR_REQUIRE(img != sd, "local_std: img and sd must not alias");
+    PAMR_TRY(check_dims(B, K, H, W));
+    PAMR_REQUIRE((long long)B * K <= 65535, "local_std: B*K must be <= 65535");
+    Dilations dil;
+    PAMR_TRY(make_dilations(dilations, nd, &dil));
+    return launch_local_std(img, sd, B, K, H, W, dil, (cudaStream_t)stream);
 }
 
 size_t pamr_propagate_scratch_bytes(int B, int C, int H, int W, const int* dilations, int nd, int iters) {
@@ -170,9 +182,9 @@ namespace {
 // workspace carve-up shared by pamr_forward_workspace_bytes and pamr_forward_f32
 struct ForwardPlan {
     AffTiling tiling;
-    size_t aff_bytes, scratch_bytes, resize_bytes, total;
+    size_t aff_bytes, scratch_bytes, resize_bytes, img_bytes, total;
 };
-ForwardPlan plan_forward(int B, int C, int H, int W, int h, int w, const Dilations& dil, int iters) {
+ForwardPlan plan_forward(int B, int K, int C, int H, int W, int h, int w, const Dilations& dil, int iters) {
     ForwardPlan p;
     const size_t HW = (size_t)H * W;
     p.tiling = tuned_tiling(B, H, W, dil);
@@ -180,17 +192,19 @@ ForwardPlan plan_forward(int B, int C, int H, int W, int h, int w, const Dilatio
     p.aff_bytes = align_up(sizeof(float) * aff_floats, 256);
     p.scratch_bytes = align_up(propagate_scratch_bytes(B, C, H, W, dil, iters, p.tiling.R > 0), 256);
     p.resize_bytes = (h != H || w != W) ? align_up(sizeof(float) * (size_t)B * C * HW, 256) : 0;
-    p.total = p.aff_bytes + p.scratch_bytes + p.resize_bytes;
+    // room for a row-pitched copy of the image (the affinity tile kernel's TMA needs 16-byte aligned rows); reserved
+    // whenever the tiled path applies, because whether the caller's base pointer is aligned is not known here
+    p.img_bytes = p.tiling.R > 0 ? align_up(affinity_pitched_image_bytes(B, K, H, W), 256) : 0;
+    p.total = p.aff_bytes + p.scratch_bytes + p.resize_bytes + p.img_bytes;
     return p;
 }
 }  // namespace
 
 size_t pamr_forward_workspace_bytes(int B, int K, int C, int H, int W, int h, int w, const int* dilations, int nd,
                                     int iters) {
-    (void)K;
     Dilations dil;
     if (make_dilations(dilations, nd, &dil) != PAMR_OK) return 0;
-    return plan_forward(B, C, H, W, h, w, dil, iters).total;
+    return plan_forward(B, K, C, H, W, h, w, dil, iters).total;
 }
 
 int pamr_forward_f32(const float* img, const float* mask, float* out, void* workspace, size_t workspace_bytes, int B,
@@ -204,7 +218,7 @@ int pamr_forward_f32(const float* img, const float* mask, float* out, void* work
     PAMR_TRY(check_dims(B, C, H, W));
     Dilations dil;
     PAMR_TRY(make_dilations(dilations, nd, &dil));
-    const ForwardPlan plan = plan_forward(B, C, H, W, h, w, dil, iters);
+    const ForwardPlan plan = plan_forward(B, K, C, H, W, h, w, dil, iters);
     if (workspace == nullptr || workspace_bytes < plan.total)
         return set_error(PAMR_ERR_WORKSPACE, "forward: workspace of %zu bytes given, %zu needed", workspace_bytes,
                          plan.total);
@@ -220,8 +234,9 @@ int pamr_forward_f32(const float* img, const float* mask, float* out, void* work
         m0 = rs;
     }
     // pamr.py:132-136 (affinity) and :138-140 (propagation loop)
-    return launch_affinity_propagate(img, K, aff, nullptr, false, m0, out, scratch, plan.scratch_bytes, B, C, H, W, dil,
-                                     iters, cls_max, dev, s);
+    float* img_pitched = plan.img_bytes ? (float*)(ws + plan.aff_bytes + plan.scratch_bytes + plan.resize_bytes) : nullptr;
+    return launch_affinity_propagate(img, K, aff, img_pitched, nullptr, false, m0, out, scratch, plan.scratch_bytes, B, C, H, W,
+                                     dil, iters, cls_max, dev, s);
 }
 
 int pamr_clean_f32(const float* m, const float* labels, float* cleaned, unsigned* cls_max, int B, int C, int h, int w,
@@ -331,6 +346,7 @@ int pamr_pseudo_labels_host_f32(const float* h_img, const float* h_mask, const f
     const size_t n_scr = propagate_scratch_bytes(B, C, h, w, dil, iters, tiling.R > 0);
     const size_t o_lab = carve(n_lab), o_aff = carve(n_aff), o_a = carve(n_mask), o_b = carve(n_scr);
     const size_t o_max = carve(n_max), o_out = carve(n_out);
+    const size_t o_pit = carve(tiling.R > 0 ? affinity_pitched_image_bytes(B, K, h, w) : 0);  // pitched copy of the image for the affinity tile kernel
     char* d = nullptr;
     cudaStream_t s = nullptr;
     PAMR_CUDA_TRY(cudaMalloc(&d, off));
@@ -350,7 +366,7 @@ int pamr_pseudo_labels_host_f32(const float* h_img, const float* h_mask, const f
             im = (const float*)(d + o_ims);
         }
         unsigned* mx = (unsigned*)(d + o_max);
-        PAMR_TRY(launch_affinity_propagate(im, K, (float*)(d + o_aff), nullptr, false, (const float*)(d + o_mask),
+        PAMR_TRY(launch_affinity_propagate(im, K, (float*)(d + o_aff), tiling.R > 0 ? (float*)(d + o_pit) : nullptr, nullptr, false, (const float*)(d + o_mask),
                                            (float*)(d + o_a), d + o_b, n_scr, B, C, h, w, dil, iters,
                                            resize ? nullptr : mx, dev, s));
         const float* lab = (h_labels && C > 1) ? (const float*)(d + o_lab) : nullptr;

@@ -207,8 +207,12 @@ int launch_local_std(const float* img, float* sd, int B, int K, int H, int W, co
 
 // Kernel launchers implemented in the .cu files (all enqueue on `s`, return a PAMR_* code).
 int launch_resize_bilinear(const float* src, float* dst, int n_planes, int h, int w, int H, int W, cudaStream_t s);
+// img_pitched: nullptr, or device scratch of affinity_pitched_image_bytes() for the tile kernel's copy of an image whose
+// rows are not 16-byte aligned (only read when affinity_image_needs_pitching())
 int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, const Dilations& dil,
-                    const AffTiling& tiling, cudaStream_t s);
+                    const AffTiling& tiling, float* img_pitched, cudaStream_t s, cudaStream_t strips_stream = nullptr);
+bool affinity_image_needs_pitching(const float* img, int W);
+size_t affinity_pitched_image_bytes(int B, int K, int H, int W);
 int launch_aff_relayout(const float* aff_std, float* aff_tiled, int B, int H, int W, const AffTiling& tiling,
                         cudaStream_t s);
 // Tiling of the tuned propagation kernel for this problem; R == 0 when only the generic kernel applies.
@@ -217,7 +221,7 @@ size_t propagate_scratch_bytes(int B, int C, int H, int W, const Dilations& dil,
 int launch_propagate(const float* aff, bool aff_is_tiled, const float* m_in, float* m_out, void* scratch,
                      size_t scratch_bytes, int B, int C, int H, int W, const Dilations& dil, int iters,
                      unsigned* cls_max, int dev, cudaStream_t s);
-int launch_affinity_propagate(const float* img, int K, float* aff_out, const float* aff_in, bool aff_is_tiled,
+int launch_affinity_propagate(const float* img, int K, float* aff_out, float* img_pitched, const float* aff_in, bool aff_is_tiled,
                               const float* m_in, float* m_out, void* scratch, size_t scratch_bytes, int B, int C, int H,
                               int W, const Dilations& dil, int iters, unsigned* cls_max, int dev, cudaStream_t s);
 int launch_clean(const float* m, const float* labels, float* cleaned, unsigned* cls_max, int B, int C, int h, int w,

@@ -191,7 +191,7 @@ size_t propagate_scratch_bytes(int B, int C, int H, int W, const Dilations& dil,
 // Affinity (optional) + `iters` propagation steps.  When img != nullptr the affinity is computed
 // here into `aff` (tile-major if the tuned kernel applies, see tuned_tiling), concurrently with the
 // repack of the input mask; otherwise `aff` is an input (standard layout unless aff_is_tiled).
-int launch_affinity_propagate(const float* img, int K, float* aff_out, const float* aff_in, bool aff_is_tiled,
+int launch_affinity_propagate(const float* img, int K, float* aff_out, float* img_pitched, const float* aff_in, bool aff_is_tiled,
                               const float* m_in, float* m_out, void* scratch, size_t scratch_bytes, int B, int C, int H,
                               int W, const Dilations& dil, int iters, unsigned* cls_max, int dev, cudaStream_t s) {
     const size_t N = (size_t)B * C * H * W;
@@ -209,7 +209,7 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
     }
     if (iters <= 0) {
         if (img != nullptr) {
-            int rc = launch_affinity(img, aff_out, B, K, H, W, dil, tiling, s);  // the caller asked for it
+            int rc = launch_affinity(img, aff_out, B, K, H, W, dil, tiling, img_pitched, s);  // the caller asked for it
             if (rc != PAMR_OK) return rc;
         }
         PAMR_CUDA_TRY(cudaMemcpyAsync(m_out, m_in, N * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -236,7 +236,7 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
     if (!tuned) {  // generic kernel: standard layout throughout, no side stream
         const float* aff = aff_in;
         if (img != nullptr) {
-            if ((rc = launch_affinity(img, aff_out, B, K, H, W, dil, tiling, s)) != PAMR_OK) return rc;
+            if ((rc = launch_affinity(img, aff_out, B, K, H, W, dil, tiling, img_pitched, s)) != PAMR_OK) return rc;
             aff = aff_out;
         }
         const float* src = m_in;
@@ -256,12 +256,14 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
     ForkJoin fj;
     if ((rc = fj.init(dev, s)) != PAMR_OK) return rc;
     if ((rc = fj.fork()) != PAMR_OK) return rc;
-    if ((rc = launch_repack_pairs(m_in, P[0], B * C, H, W, fj.r->side)) != PAMR_OK) return rc;
     const float* aff = aff_in;
     if (img != nullptr) {
-        if ((rc = launch_affinity(img, aff_out, B, K, H, W, dil, tiling, s)) != PAMR_OK) return rc;
+        // (the strips of the affinity layout go to the side stream, in front of the mask repack)
+        if ((rc = launch_affinity(img, aff_out, B, K, H, W, dil, tiling, img_pitched, s, fj.r->side)) != PAMR_OK) return rc;
         aff = aff_out;
-    } else if (!aff_is_tiled) {
+    }
+    if ((rc = launch_repack_pairs(m_in, P[0], B * C, H, W, fj.r->side)) != PAMR_OK) return rc;
+    if (img == nullptr && !aff_is_tiled) {
         float* at = (float*)((char*)scratch + 2 * plan.pingpong_each);
         if ((rc = launch_aff_relayout(aff_in, at, B, H, W, tiling, s)) != PAMR_OK) return rc;
         aff = at;
@@ -285,7 +287,7 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, const flo
 int launch_propagate(const float* aff, bool aff_is_tiled, const float* m_in, float* m_out, void* scratch,
                      size_t scratch_bytes, int B, int C, int H, int W, const Dilations& dil, int iters,
                      unsigned* cls_max, int dev, cudaStream_t s) {
-    return launch_affinity_propagate(nullptr, 0, nullptr, aff, aff_is_tiled, m_in, m_out, scratch, scratch_bytes, B, C, H,
+    return launch_affinity_propagate(nullptr, 0, nullptr, nullptr, aff, aff_is_tiled, m_in, m_out, scratch, scratch_bytes, B, C, H,
                                      W, dil, iters, cls_max, dev, s);
 }
 

@@ -906,17 +906,6 @@ inline bool row_strip_in_tail(long long items, long long ntiles, int grid) {
     return (items + warps - 1) / warps <= TAIL_ITEMS_MAX;
 }
 
-int device_sm_count(int dev, int* out) {
-    static std::atomic<int> cache[64];
-    int n = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
-    if (n == 0) {
-        PAMR_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-        if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
-    }
-    *out = n;
-    return PAMR_OK;
-}
-
 template <int R>
 int launch_one(const float* aff, const AffTiling& tiling, const float* src, int src_pitch, float* dst, int dst_pitch,
                bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int sm_count, int dev, cudaStream_t s) {
@@ -972,6 +961,17 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
 }
 
 }  // namespace
+
+int device_sm_count(int dev, int* out) {
+    static std::atomic<int> cache[64];
+    int n = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
+    if (n == 0) {
+        PAMR_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 64) cache[dev].store(n, std::memory_order_relaxed);
+    }
+    *out = n;
+    return PAMR_OK;
+}
 
 // 1-D map over a flat fp32 array (pamr_affinity.cu: image rows are fetched one box of `box` floats at a time, at any
 // 4-byte offset -- W needs no alignment; only the base must be 16-byte aligned).  `map` points at a CUtensorMap.

@@ -71,3 +71,57 @@ class ShardedPseudoLabeler:
         if not gather or world == 1:
             return local
         return gather_labels(local, B, self.group)
+
+
+class OverlappedLabelGather:
+    """All-gather of the per-rank uint8 label maps on a SIDE stream, so that the collective of step i runs next to
+    the kernels of step i+1 ("overlap with the final epilogue tile wave").
+
+    submit(local) enqueues, on the side stream, an all_gather_into_tensor of `local` ([b,H,W] uint8, the same shape
+    on every rank) into one of `depth` rotating output buffers -- ordered after everything enqueued so far on the
+    caller's current stream -- and returns that buffer ([world*b,H,W]).  With host_out (pinned) the gathered maps are
+    also copied to the host on the side stream.  The caller's stream does NOT wait: call wait() before reading the
+    returned buffer (or host_out) and before the buffer comes round again (depth submits later).
+    On CPU tensors (gloo, the unit tests) the gather is synchronous."""
+
+    def __init__(self, device, group=None, depth=2):
+        self.device = torch.device(device)
+        self.group = group
+        self.depth = int(depth)
+        self.cuda = self.device.type == "cuda"
+        self.side = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self._bufs = {}
+        self._n = 0
+
+    def _buffer(self, local, world):
+        key = (tuple(local.shape), local.dtype)
+        if key not in self._bufs:
+            if self.cuda:  # the old buffers may still be in flight
+                self.side.synchronize()
+            shape = (world * local.shape[0],) + tuple(local.shape[1:])
+            self._bufs = {key: [torch.empty(shape, dtype=local.dtype, device=local.device) for _ in range(self.depth)]}
+        buf = self._bufs[key][self._n % self.depth]
+        self._n += 1
+        return buf
+
+    def submit(self, local, host_out=None):
+        world = dist.get_world_size(self.group)
+        out = self._buffer(local, world)
+        if not self.cuda:
+            dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+            if host_out is not None:
+                host_out.copy_(out)
+            return out
+        main = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            dist.all_gather_into_tensor(out, local, group=self.group)
+            if host_out is not None:
+                host_out.copy_(out, non_blocking=True)
+        local.record_stream(self.side)  # the allocator must not hand `local` out again before the gather has read it
+        return out
+
+    def wait(self):
+        """Everything submitted so far becomes visible to the caller's current stream."""
+        if self.cuda:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)

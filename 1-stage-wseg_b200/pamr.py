@@ -73,6 +73,10 @@ class LocalStDev(LocalAffinity):
     def _init_aff(self):
         return _shift_kernel(0.0, 1.0, True)
 
+    def forward(self, x):
+        """x [B,K,H,W] -> unbiased std over the 9*nd samples, [B,K,1,H,W] like the reference (pamr.py:98-103)."""
+        return local_std(x, self.dilations).unsqueeze(2)
+
 
 class LocalAffinityAbs(LocalAffinity):
     """pamr.py:105-109: |centre - neighbour|."""
@@ -123,6 +127,16 @@ def local_affinity(x, dilations):
     aff = torch.empty((B, 8 * nd, H, W), dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().pamr_affinity_f32(x.data_ptr(), aff.data_ptr(), B, K, H, W, d, nd, _dev(x), _stream(x.device)))
     return aff
+
+
+def local_std(x, dilations):
+    """LocalStDev (pamr.py:77-103): image [B,K,H,W] -> unbiased std over the 9*nd samples, [B,K,H,W]."""
+    x = _check_cuda_f32("x", x)
+    B, K, H, W = x.shape
+    d, nd = _dil_array(dilations)
+    sd = torch.empty_like(x)
+    _lib.check(_lib.lib().pamr_local_std_f32(x.data_ptr(), sd.data_ptr(), B, K, H, W, d, nd, _dev(x), _stream(x.device)))
+    return sd
 
 
 def propagate(aff, mask, dilations, num_iter, return_class_max=False):

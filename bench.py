@@ -4,11 +4,20 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1, one rank per GPU)
 
-A step = run_pamr -> _rescale_and_clean -> pseudo_gtmask -> argmax ("PAMR + clean/argmax epilogue as
-in stage_net", BASELINE.json configs[1]) over one synthetic batch of B=16 per GPU, 3x321x321 images,
-21-class masks at image resolution.  Weak scaling: every rank processes its own B=16 shard
-(configs[4]: B=128 over 8 GPUs) and the uint8 label maps are all-gathered with NCCL inside the step.
-Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for the definitions of each key.
+A step = run_pamr -> _rescale_and_clean -> pseudo_gtmask -> argmax ("PAMR + clean/argmax epilogue as in
+stage_net", BASELINE.json configs[1]) over one synthetic batch of B=16 per GPU, 3x321x321 images, 21-class masks at
+image resolution.  Weak scaling: every rank processes its own B=16 shard (configs[4]: B=128 over 8 GPUs); the uint8
+label maps are all-gathered with NCCL inside the step, on a side stream, so that the gather of step i overlaps the
+affinity kernel of step i+1.  Rank 0 prints ONE JSON line; besides the headline it carries
+  roofline        the propagation launch against the measured HBM peak (+ the binding on-chip roof, from ncu)
+  e2e             the same step from pinned HOST buffers through HostPipeline (H2D + D2H inside the timed region)
+  e2e_real_shape  the shape stage_net really calls it with: masks at 81x81 uploaded, up-sampling on the device
+  small_map       PAMR.forward at stage_net's mask sizes (the resident kernel: one launch for all iterations)
+  configs         BASELINE.json configs[2], [3] and [4]-on-one-GPU (N = 1 only)
+  strong          configs[4] as stated: B=128 in total, split over the N GPUs
+  allgather       the NCCL gather alone (N > 1)
+  cpu_baseline    the CPU port of the reference path on the host cores (N = 1 only)
+See DESIGN.md "Measurement" for the definitions.
 """
 import argparse
 import json
@@ -26,6 +35,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 D6 = [1, 2, 4, 8, 12, 24]
 B_PER_GPU, K_IMG, C_CLS, H_IMG, W_IMG, ITERS = 16, 3, 21, 321, 321, 10
+B_STRONG = 128  # BASELINE.json configs[4]
 P_TAPS = 8 * len(D6)
 METRIC = "PAMR Mpix/s (21 cls, 10 iters)"
 UNIT = "Mpix/s"
@@ -34,12 +44,27 @@ BYTES_PER_PIXEL_PROPAGATE = 4 * (P_TAPS + 2 * C_CLS)
 HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
+def step_bytes_per_pixel(K=K_IMG, C=C_CLS, iters=ITERS):
+    """Algorithmic HBM bytes of the whole step per pixel: affinity (K + P) + iters * (P + 2C) + epilogue (C + 1/4)."""
+    return 4 * (K + P_TAPS + iters * (P_TAPS + 2 * C)) + 4 * C + 1
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_facts():
+    """DRAM traffic and shared-memory pipe utilisation of the propagation kernel from the committed ncu capture of
+    this build (profiles/propagate_ncu_facts.json, written by tools/ncu_facts.py from the .ncu-rep)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "propagate_ncu_facts.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -89,9 +114,9 @@ class ClockSampler:
 
 
 def bind_to_gpu_numa_node(index):
-    """Multi-GPU runs: pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity), so that
-    the pinned staging buffers of the end-to-end path are first-touched on that NUMA node and the N concurrent
-    host->device streams do not cross sockets.  Best effort: silently skipped if NVML is unavailable."""
+    """Multi-GPU runs: pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any
+    pinned buffer is allocated, so that the staging buffers of the end-to-end path are first-touched on that NUMA
+    node.  Best effort: silently skipped if NVML is unavailable."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -100,15 +125,16 @@ def bind_to_gpu_numa_node(index):
         pass
 
 
-def cpu_baseline_sample(steps, warmup):
-    """Times the CPU port of the reference path (oracle/pamr_oracle.c, OpenMP over all host cores) on a
-    bounded sample of the workload: one 321x321 image of the batch per step."""
+def cpu_baseline_sample(steps, warmup, images_per_step=1):
+    """Times the CPU port of the reference path (oracle/pamr_oracle.c, OpenMP over all host cores) on a bounded
+    sample of the workload: `images_per_step` 321x321 images of the batch per step."""
     import numpy as np
     import synth
     from oracle import oracle
-    img = synth.image_uniform(1, K_IMG, H_IMG, W_IMG, 0)
-    msk = synth.mask_softmax(1, C_CLS, H_IMG, W_IMG, 1)
-    lab = synth.labels_bernoulli(1, C_CLS, 2, p=0.3)
+    n = images_per_step
+    img = synth.image_uniform(n, K_IMG, H_IMG, W_IMG, 0)
+    msk = synth.mask_softmax(n, C_CLS, H_IMG, W_IMG, 1)
+    lab = synth.labels_bernoulli(n, C_CLS, 2, p=0.3)
     # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
     try:
         oracle.set_num_threads(len(os.sched_getaffinity(0)))
@@ -127,11 +153,12 @@ def cpu_baseline_sample(steps, warmup):
     for _ in range(steps):
         out = step()
     dt = (time.perf_counter() - t0) / steps
-    assert out.shape == (1, H_IMG, W_IMG) and out.dtype == np.uint8
-    return {"value": H_IMG * W_IMG / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "B=1 of the batch (1x3x%dx%d image, %d classes, %d iterations, PAMR + clean/argmax), "
-                      "%d timed steps, OpenMP C port of the reference path" % (H_IMG, W_IMG, C_CLS, ITERS, steps),
-            "ms_per_image": dt * 1e3}
+    assert out.shape == (n, H_IMG, W_IMG) and out.dtype == np.uint8
+    return {"value": n * H_IMG * W_IMG / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "B=%d of the batch per step (%dx%dx%dx%d image, %d classes, %d iterations, PAMR + clean/argmax), "
+                      "%d timed steps after %d warm-up, OpenMP C port of the reference path"
+                      % (n, n, K_IMG, H_IMG, W_IMG, C_CLS, ITERS, steps, warmup),
+            "ms_per_step": dt * 1e3}
 
 
 def config_dict(n_gpus):
@@ -139,22 +166,29 @@ def config_dict(n_gpus):
                         "resolution, PAMR(%d, %s) + clean/argmax epilogue" % (B_PER_GPU, K_IMG, H_IMG, W_IMG, C_CLS,
                                                                               ITERS, D6),
             "global_batch": B_PER_GPU * n_gpus, "per_gpu_batch": B_PER_GPU, "parallelism": "batch-shard dp%d" % n_gpus,
-            "collective": "NCCL all-gather of uint8 labels" if n_gpus > 1 else "none",
+            "collective": "NCCL all-gather of uint8 labels on a side stream (overlaps the next step)" if n_gpus > 1 else "none",
             "l2_policy": "no flush: inputs+scratch per step (%.0f MB) exceed the 126 MB L2"
                          % (4e-6 * B_PER_GPU * H_IMG * W_IMG * (K_IMG + 3 * C_CLS + P_TAPS))}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (here the oracle port; the
-    reference is pure Python and cannot travel to the GPU box), all host threads, rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path (here the C port in oracle/; the reference is
+    pure Python and cannot travel to the GPU box), all host threads, rank 0 only.  A step is a bounded sample of the
+    b200 arm's per-step workload: one 321x321 image per GPU of the run (N images at --gpus N), so that the per-N
+    ratio of the two arms compares like with like while the host's core count stays what it is."""
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 40)), max(1, min(args.warmup, 3))
-    base = cpu_baseline_sample(steps, warmup)
+    n = max(1, args.gpus)
+    base = cpu_baseline_sample(max(1, args.steps), max(0, args.warmup), images_per_step=n)
+    cfg = config_dict(args.gpus)
+    cfg["workload"] = ("bounded sample of configs[1]: B=%d per step (1 image of the %d per GPU, x %d GPU(s)), %dx%dx%d, %d classes, "
+                       "PAMR(%d, %s) + clean/argmax epilogue on the host CPU" % (n, B_PER_GPU, n, K_IMG, H_IMG, W_IMG, C_CLS, ITERS, D6))
+    cfg["sample_batch"] = n
+    cfg["collective"] = "none"
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": base["ms_per_image"], "higher_is_better": True,
+            "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": base["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args.gpus), "cpu_baseline": base,
+            "config": cfg, "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -167,6 +201,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="headline + roofline + e2e only (no configs / small maps / strong)")
     ap.add_argument("--only", default="", help="profiling aid: 'step' runs only the timed step loop")
     args = ap.parse_args()
 
@@ -181,6 +216,8 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__)]
         raise SystemExit(subprocess.call(cmd + sys.argv[1:]))
 
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)  # before torch allocates anything pinned
     import torch
     import torch.distributed as dist
     import wseg_b200
@@ -190,7 +227,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        bind_to_gpu_numa_node(local_rank)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank if world > 1 else 0)
@@ -198,28 +234,36 @@ def main():
     args.warmup = max(args.warmup, 3)
     B, K, C, H, W = B_PER_GPU, K_IMG, C_CLS, H_IMG, W_IMG
     npix = B * H * W
+    peak, peak_src = hbm_peak()
 
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    image = torch.rand((B, K, H, W), generator=gen, device=dev)
-    mask = torch.softmax(2.0 * torch.randn((B, C, H, W), generator=gen, device=dev), 1)
-    labels = (torch.rand((B, C - 1), generator=gen, device=dev) < 0.3).float()
-    labels[:, 0] = 1.0
+    def synth_inputs(b, h_img, w_img, h_msk, w_msk, seed):
+        gen = torch.Generator(device=dev).manual_seed(seed + rank)
+        image = torch.rand((b, K, h_img, w_img), generator=gen, device=dev)
+        mask = torch.softmax(2.0 * torch.randn((b, C, h_msk, w_msk), generator=gen, device=dev), 1)
+        labels = (torch.rand((b, C - 1), generator=gen, device=dev) < 0.3).float()
+        labels[:, 0] = 1.0
+        return image, mask, labels
+
+    image, mask, labels = synth_inputs(B, H, W, H, W, 1234)
     pamr = wseg_b200.PAMR(ITERS, D6).to(dev)
-    gathered = torch.empty((world * B, H, W), dtype=torch.uint8, device=dev) if world > 1 else None
+    pamr_2x = wseg_b200.PAMR(2 * ITERS, D6).to(dev)
+    gather = wseg_b200.OverlappedLabelGather(dev) if world > 1 else None
 
     def step(img, msk, lab):
         out = wseg_b200.refine_and_label(pamr, img, msk, lab)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
-            return gathered
+            return gather.submit(out)  # NCCL all-gather on the side stream; the next step's kernels do not wait for it
         return out
 
     def barrier():
         if world > 1:
+            gather.wait()
             dist.barrier()
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
+        """Device time of `steps` calls (CUDA events on the launching stream, barrier + synchronize on both sides,
+        maximum over the ranks).  Returns (ms per call, kernels launched by libpamr_b200 in the timed region)."""
         for _ in range(warmup):
             fn()
         barrier()
@@ -228,6 +272,8 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        if world > 1:
+            gather.wait()  # the last gathers belong to the timed region
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -236,6 +282,15 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms / steps, _lib.launch_count() - n0
+
+    def propagate_roofline(pm, pm2, img, msk, n, b_, h_, w_):
+        """Marginal cost of one propagation launch inside the forward path, (t(2*ITERS) - t(ITERS)) / ITERS, and what
+        that is of the HBM roofline (360 B per pixel and launch)."""
+        t1, _ = timed(lambda: pm(img, msk), n, 2)
+        t2, _ = timed(lambda: pm2(img, msk), n, 2)
+        ms = (t2 - t1) / ITERS
+        gbs = BYTES_PER_PIXEL_PROPAGATE * b_ * h_ * w_ / (ms * 1e-3) / 1e9
+        return ms, t1, gbs
 
     # ---- device-resident throughput (`value`)
     sampler = ClockSampler(dev.index)
@@ -254,51 +309,100 @@ def main():
             print(json.dumps({"ms_per_step": ms_step, "launches_per_step": launches / args.steps}))
         return
 
-    # ---- dominant kernel: the propagation launch (ITERS of them per step).  Its average duration is
-    # measured live, with CUDA events on the launching stream, as the marginal cost of a launch inside
-    # the forward path: (t_forward(2*ITERS) - t_forward(ITERS)) / ITERS.  (Same kernels, same layout,
-    # no relayout/repack in the difference; the remainder-strip kernel runs concurrently on a side stream.)
-    pamr_2x = wseg_b200.PAMR(2 * ITERS, D6).to(dev)
+    # ---- dominant kernel: the propagation launch (ITERS of them per step), timed live with CUDA events
     nrep = max(5, args.steps // 2)
-    ms_fwd, _ = timed(lambda: pamr(image, mask), nrep, 3)
-    ms_fwd2, _ = timed(lambda: pamr_2x(image, mask), nrep, 3)
-    ms_launch = (ms_fwd2 - ms_fwd) / ITERS
+    ms_launch, ms_fwd, achieved = propagate_roofline(pamr, pamr_2x, image, mask, nrep, B, H, W)
     ms_aff, _ = timed(lambda: wseg_b200.local_affinity(image, D6), nrep, 3)
     dec, cmax = pamr(image, mask, return_class_max=True)
-    ms_epi, _ = timed(lambda: wseg_b200.pseudo_labels(dec, labels, None, cmax), max(5, args.steps // 2), 3)
-    peak, peak_src = hbm_peak()
-    achieved = BYTES_PER_PIXEL_PROPAGATE * npix / (ms_launch * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "propagate_dram_bytes.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    ms_epi, _ = timed(lambda: wseg_b200.pseudo_labels(dec, labels, None, cmax), nrep, 3)
+    facts = ncu_facts()
     roofline = {"bound": "hbm", "kernel": "propagate (one of %d launches per step)" % ITERS, "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": facts.get("dram_bytes_per_launch"),
+                "traffic_source": facts.get("source"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_PIXEL_PROPAGATE * npix,
-                "ms_per_launch": ms_launch, "ms_forward": ms_fwd, "ms_affinity_standard_layout": ms_aff, "ms_epilogue": ms_epi,
-                "whole_step_GBps": (4 * (K + P_TAPS + ITERS * (P_TAPS + 2 * C)) + 4 * C + 1) * npix / (ms_step * 1e-3) / 1e9}
+                "ms_per_launch": ms_launch, "ms_forward": ms_fwd,
+                "ms_forward_other_than_propagation": ms_fwd - ITERS * ms_launch,
+                "ms_affinity_standard_layout": ms_aff, "ms_epilogue": ms_epi,
+                "whole_step_GBps": step_bytes_per_pixel() * npix / (ms_step * 1e-3) / 1e9,
+                # the on-chip resource that binds this kernel is the shared-memory pipe, not HBM
+                "secondary_roof": {"resource": "shared-memory pipe (LDS wavefronts)", "lds_pct": facts.get("lds_pct"),
+                                   "ceiling": facts.get("lds_ceiling_frac_of_hbm_roofline"),
+                                   "source": facts.get("source")}}
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
-    h_image, h_mask, h_labels = image.cpu().pin_memory(), mask.cpu().pin_memory(), labels.cpu().pin_memory()
-    h_out = torch.empty((world * B if world > 1 else B, H, W), dtype=torch.uint8).pin_memory()
-
-    # public host-input API: chunked H2D copies overlapped with the kernels (wseg_b200.HostPipeline)
+    n_e2e = max(20, args.steps // 3)
     pipe = wseg_b200.HostPipeline(pamr, dev, chunks=int(os.environ.get("PAMR_BENCH_CHUNKS", "1")))
-    d_local = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
 
-    def e2e_step():
+    def e2e_record(h_image, h_mask, h_labels):
+        h_out = torch.empty((world * B if world > 1 else B, H, W), dtype=torch.uint8).pin_memory()
+        d_local = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+
+        def e2e_step():
+            if world == 1:
+                pipe(h_image, h_mask, h_labels, h_out, out_size=(H, W))
+            else:  # per-rank shard through the pipeline, the NCCL gather of the labels and the D2H on the side stream
+                pipe(h_image, h_mask, h_labels, d_out=d_local, out_size=(H, W))
+                gather.submit(d_local, host_out=h_out)
+
+        ms, _ = timed(e2e_step, n_e2e, 3)
+        h2d = h_image.numel() * 4 + h_mask.numel() * 4 + h_labels.numel() * 4
+        return {"value": world * npix / (ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": h_out.numel(), "ms_per_step": ms, "steps": n_e2e}
+
+    e2e = e2e_record(image.cpu().pin_memory(), mask.cpu().pin_memory(), labels.cpu().pin_memory())
+    # the shape stage_net really calls the path with (SoftMaxAE.py:176-179, 250-259): masks at 81x81 for a 321x321 crop;
+    # the image resize, PAMR at 81x81 (resident kernel), up-sampling + clean + labels at 321x321 all run on the device
+    _, mask_lo, _ = synth_inputs(B, H, W, 81, 81, 4321)
+    e2e_real = e2e_record(image.cpu().pin_memory(), mask_lo.cpu().pin_memory(), labels.cpu().pin_memory())
+    e2e_real["workload"] = "B=%d per GPU, image %dx%d and masks 81x81 uploaded, labels %dx%d downloaded" % (B, H, W, H, W)
+    ms_real_dev, _ = timed(lambda: step(image, mask_lo, labels), nrep, 3)
+    e2e_real["device_resident_ms_per_step"] = ms_real_dev
+
+    extras = {}
+    if not args.no_extras:
+        # ---- stage_net's own PAMR call shapes: the resident small-map kernel (affinity + all iterations in one launch)
+        small = []
+        for hw in (41, 81):
+            im_s, mk_s, _ = synth_inputs(B, hw, hw, hw, hw, 777 + hw)
+            ms_s, l_s = timed(lambda: pamr(im_s, mk_s), max(20, nrep), 5)
+            small.append({"shape": "B=%d %dx%d, %d classes, %d iterations" % (B, hw, hw, C, ITERS), "ms_forward": ms_s,
+                          "launches_per_forward": l_s / max(20, nrep), "mpix_s": B * hw * hw / (ms_s * 1e-3) / 1e6,
+                          "whole_forward_GBps": (step_bytes_per_pixel() - 4 * C - 1) * B * hw * hw / (ms_s * 1e-3) / 1e9})
+            del im_s, mk_s
+        extras["small_map"] = small
+
+        def config_record(name, b_, h_, w_, n):
+            img_c, msk_c, lab_c = synth_inputs(b_, h_, w_, h_, w_, 99 + h_ + b_)
+            ms_c, _ = timed(lambda: wseg_b200.refine_and_label(pamr, img_c, msk_c, lab_c), n, 2)
+            ms_l, ms_f, gbs = propagate_roofline(pamr, pamr_2x, img_c, msk_c, max(3, n // 2), b_, h_, w_)
+            rec = {"name": name, "ms_per_step": ms_c, "mpix_s": b_ * h_ * w_ / (ms_c * 1e-3) / 1e6,
+                   "ms_per_propagate_launch": ms_l, "propagate_GBps": gbs, "frac": gbs / peak,
+                   "whole_step_GBps": step_bytes_per_pixel() * b_ * h_ * w_ / (ms_c * 1e-3) / 1e9}
+            del img_c, msk_c, lab_c
+            torch.cuda.empty_cache()
+            return rec
+
+        # ---- BASELINE.json configs[4] as stated: B=128 in total, split over the GPUs of this run
+        b_strong = B_STRONG // world
+        img_s, msk_s, lab_s = synth_inputs(b_strong, H, W, H, W, 555)
+        ms_strong, _ = timed(lambda: step(img_s, msk_s, lab_s), max(5, min(args.steps, 20)), 2)
+        extras["strong"] = {"global_batch": B_STRONG, "per_gpu_batch": b_strong, "ms_per_step": ms_strong,
+                            "value": B_STRONG * H * W / (ms_strong * 1e-3) / 1e6, "unit": UNIT,
+                            "whole_step_GBps_per_gpu": step_bytes_per_pixel() * b_strong * H * W / (ms_strong * 1e-3) / 1e9}
+        del img_s, msk_s, lab_s
+        torch.cuda.empty_cache()
         if world == 1:
-            pipe(h_image, h_mask, h_labels, h_out)
-        else:  # per-rank shard through the pipeline, then the NCCL gather of the labels, then D2H
-            pipe(h_image, h_mask, h_labels, d_out=d_local)
-            dist.all_gather_into_tensor(gathered, d_local)
-            h_out.copy_(gathered, non_blocking=True)
-
-    ms_e2e, _ = timed(e2e_step, max(3, args.steps // 3), 3)
-    h2d = h_image.numel() * 4 + h_mask.numel() * 4 + h_labels.numel() * 4
-    d2h = h_out.numel()
+            recs = [config_record("configs[2] multi-scale inference, B=1 %dx%d" % (s, s), 1, s, s, 10) for s in (256, 512, 768, 1024)]
+            recs.append(config_record("configs[3] high resolution, B=8 1024x2048", 8, 1024, 2048, 5))
+            recs.append(config_record("configs[4] on one GPU, B=128 321x321", B_STRONG, H, W, 5))
+            extras["configs"] = recs
+        else:
+            # ---- the collective alone: all-gather of this step's uint8 labels (not overlapped with anything)
+            lab_u8 = wseg_b200.refine_and_label(pamr, image, mask, labels)
+            buf = torch.empty((world * B, H, W), dtype=torch.uint8, device=dev)
+            ms_ag, _ = timed(lambda: dist.all_gather_into_tensor(buf, lab_u8), 50, 5)
+            extras["allgather"] = {"ms": ms_ag, "bytes_per_rank": lab_u8.numel(), "overlapped_in_step": True,
+                                   "note": "issued on a side stream; the next step's kernels start without waiting for it"}
 
     if world > 1:
         dist.barrier()
@@ -309,10 +413,9 @@ def main():
     line = {"metric": METRIC, "value": world * npix / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world),
-            "roofline": roofline, "clocks": clocks,
-            "e2e": {"value": world * npix / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+            "roofline": roofline, "clocks": clocks, "e2e": e2e, "e2e_real_shape": e2e_real,
             "gpu_launches": launches}
+    line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(20, 2)
     else:

@@ -74,6 +74,14 @@ int pamr_affinity_f32(const float* img, float* aff, int B, int K, int H, int W, 
                       int nd, int dev, pamr_stream_t stream);
 
 /*
+ * LocalStDev.forward (pamr.py:77-103) on its own: unbiased standard deviation over the 9*nd samples
+ * (3x3 neighbourhood incl. the centre at every dilation, replicate padding) of every pixel and channel.
+ * img [B,K,H,W] -> sd [B,K,H,W]  (the reference returns the same values as [B,K,1,H,W]).  B*K <= 65535.
+ */
+int pamr_local_std_f32(const float* img, float* sd, int B, int K, int H, int W, const int* dilations,
+                       int nd, int dev, pamr_stream_t stream);
+
+/*
  * `iters` propagation steps.  Replaces the loop pamr.py:138-140 (LocalAffinityCopy :57-75):
  *   M'[b,c,y,x] = sum_p aff[b,p,y,x] * M[b,c,clamp(y+dy_p),clamp(x+dx_p)].
  * aff [B,8*nd,H,W]; m_in [B,C,H,W] (never written); m_out [B,C,H,W] receives the result;

@@ -166,6 +166,48 @@ def test_gather_labels_gloo_world2(batch):
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def _overlapped_gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = wseg_b200.OverlappedLabelGather("cpu", depth=2)
+        ok = True
+        outs = []
+        for step in range(5):  # the two output buffers rotate: results of steps i and i+1 are alive together
+            full = ((torch.arange(world * 2 * 3 * 4, dtype=torch.int64) + 7 * step) % 251).to(torch.uint8).view(world * 2, 3, 4)
+            host = torch.empty_like(full)
+            out = g.submit(full[2 * rank: 2 * rank + 2].clone(), host_out=host)
+            g.wait()
+            ok = ok and bool(torch.equal(out, full)) and bool(torch.equal(host, full))
+            outs.append((out, full))
+            if len(outs) >= 2:
+                ok = ok and bool(torch.equal(outs[-2][0], outs[-2][1]))  # the previous step's buffer is still intact
+        ok = ok and outs[-1][0].data_ptr() == outs[-3][0].data_ptr() != outs[-2][0].data_ptr()
+        # a rank with an empty shard (B < world) still takes part in the gather of ShardedPseudoLabeler
+        empty = wseg_b200.gather_labels(torch.full((1 if rank == 0 else 0, 2, 2), 9, dtype=torch.uint8), 1)
+        ok = ok and tuple(empty.shape) == (1, 2, 2) and int(empty.sum()) == 36
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_gather_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_overlapped_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def _build_c_demo(tmp_path):
     import shutil
     import subprocess

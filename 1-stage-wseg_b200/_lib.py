@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PAMR_B200_LIB selects another build of the same ABI (experiment variants, tools/build_variant.sh)
 LIB_PATH = os.environ.get("PAMR_B200_LIB") or os.path.join(_HERE, "libpamr_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lock = threading.Lock()
 _lib = None
@@ -39,7 +39,7 @@ SIGNATURES = {
     "pamr_pseudo_labels_host_f32": (_i, [_vp] * 4 + [_i] * 7 + [_vp, _i, _i, _f, _f, _f, _i]),
     "pamr_denorm_resize_f32": (_i, [_vp] * 4 + [_i] * 6 + [_i, _vp]),
     "pamr_merge_multiscale_f32": (_i, [_vp] * 5 + [_i] * 7 + [_f, _f, _i, _vp]),
-    "pamr_mask_ce_workspace_bytes": (ctypes.c_size_t, [_i] * 4),
+    "pamr_mask_ce_workspace_bytes": (ctypes.c_size_t, [_i] * 6),
     "pamr_labels_from_onehot_f32": (_i, [_vp, _vp, _vp] + [_i] * 4 + [_i, _vp]),
     "pamr_mask_ce_forward_f32": (_i, [_vp] * 6 + [ctypes.c_size_t] + [_i] * 6 + [_i, _vp]),
     "pamr_mask_ce_backward_f32": (_i, [_vp] * 5 + [ctypes.c_size_t] + [_i] * 6 + [_i, _vp]),

@@ -283,9 +283,9 @@ int pamr_merge_multiscale_f32(const float* masks, const int* pads_host, const fl
                                    prospect_thresh, (cudaStream_t)stream);
 }
 
-size_t pamr_mask_ce_workspace_bytes(int B, int C, int H, int W) {
+size_t pamr_mask_ce_workspace_bytes(int B, int C, int h, int w, int H, int W) {
     if (B < 1 || C < 1 || H < 1 || W < 1) return 0;
-    return mask_ce_workspace_bytes(B, C, H, W);
+    return mask_ce_workspace_bytes(B, C, h, w, H, W);
 }
 
 int pamr_labels_from_onehot_f32(const float* pseudo_gt, uint8_t* label, int* class_count, int B, int C, int H, int W,

@@ -232,7 +232,7 @@ int launch_merge_multiscale(const float* masks, const int* pads_host, const floa
                             int S, int C, int Hp, int Wp, int H, int W, int flip, float bg_pow, float thresh,
                             cudaStream_t s);
 // pamr_loss.cu (balanced_mask_loss_ce)
-size_t mask_ce_workspace_bytes(int B, int C, int H, int W);
+size_t mask_ce_workspace_bytes(int B, int C, int h, int w, int H, int W);
 int launch_labels_from_onehot(const float* pseudo_gt, uint8_t* label, int* class_count, int B, int C, int H, int W,
                               cudaStream_t s);
 int launch_mask_ce_forward(const float* logits, const uint8_t* label, const int* class_count, const float* gt_labels,

@@ -6,12 +6,20 @@
 //   loss[b] = bw[b] * mean_px( cw[b,label] * (logsumexp_c z - z[label]) )           (:77, :86)
 // and d(sum_b g[b] loss[b]) / d logits through the transpose of the interpolation.
 //
-// Forward: one thread per label pixel, online log-sum-exp over the C interpolated logits, per-batch
-// sum in double (warp shuffle -> block -> one atomicAdd(double) per block); it also leaves lse(px) and
-// coef(px) = cw[label]/(H*W) (0 where ignored) in the workspace.
-// Backward: gather, deterministic, no atomics: one thread per logit element (b,c,i,j) visits the label
-// pixels whose bilinear footprint touches (i,j) (about (2*scale)^2 of them), recomputes z_c there and
-// adds coef * (exp(z_c - lse) - [c == label]) * wy * wx.
+// Forward (one launch + one small memset): one thread per label pixel; the C interpolated logits go through an
+// online log-sum-exp in base 2 (ex2.approx, 2 ulp); the class weights come from the counts (per block, in shared
+// memory); per-image sum in double (warp shuffle -> block -> one atomicAdd(double) per block) and the block that
+// arrives last at the image's ticket writes loss[b].  lse(px) and coef(px) = cw[label]/(H*W) (0 where ignored) stay
+// in the workspace for the backward pass.
+// Backward, deterministic, no atomics:
+//   same resolution:  one thread per pixel, grad_c = g * coef * (2^((z_c - lse) log2 e) - [c == label]);
+//   with up-/down-sampling: the transposed bilinear interpolation is separable, so it runs as two gathers --
+//     T[b,c,y,j]    = sum_x coef(y,x) * (softmax_c(y,x) - [c == label(y,x)]) * wx(x -> j)      (label rows, logit columns)
+//     grad[b,c,i,j] = g_b * sum_y T[b,c,y,j] * wy(y -> i)
+//   the first with the six logits a thread needs held in registers (its source column and the two next to it, on the
+//   two source rows of label row y), so that the inner loop over the ~2/scale pixels of its footprint has no
+//   dependent loads.  (Round 1 visited the whole 2-D footprint per logit element and recomputed bilerp + expf for
+//   each of its ~(2/scale)^2 pixels: 0.55 ms at 81x81 -> 321x321.)
 #include "pamr_common.cuh"
 
 namespace pamr {
@@ -22,21 +30,34 @@ constexpr int LS_BX = 32, LS_BY = 8;
 constexpr int CE_BATCH = 7;  // class planes loaded per batch in the forward kernel (21 = 3 x 7)
 
 struct CeWorkspace {
-    double* acc;   // [B]    sum_px cw*ce
-    float* cwbw;   // [B, C+1]  cw[b,0..C-1], bw[b]
-    float* lse;    // [B,H,W]
-    float* coef;   // [B,H,W]
+    double* acc;     // [B]    sum_px cw*ce
+    unsigned* ticket;// [B]    blocks of image b that have added their sum
+    float* bw;       // [B]    batch weight (written by the forward pass)
+    float* lse;      // [B,H,W]
+    float* coef;     // [B,H,W]
+    float* T;        // [B,C,H,w]  backward with resampling: the gradient after the x pass
+    size_t head_bytes;  // acc + ticket: zeroed by one memset before the forward kernel
 };
 __host__ __device__ inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
-inline CeWorkspace carve(void* ws, int B, int C, int H, int W) {
+inline CeWorkspace carve(void* ws, int B, int H, int W) {
     char* p = (char*)ws;
     CeWorkspace r;
     r.acc = (double*)p; p += up256(sizeof(double) * B);
-    r.cwbw = (float*)p; p += up256(sizeof(float) * (size_t)B * (C + 1));
+    r.ticket = (unsigned*)p; p += up256(sizeof(unsigned) * B);
+    r.head_bytes = (size_t)(p - (char*)ws);
+    r.bw = (float*)p; p += up256(sizeof(float) * B);
     r.lse = (float*)p; p += up256(sizeof(float) * (size_t)B * H * W);
-    r.coef = (float*)p;
+    r.coef = (float*)p; p += up256(sizeof(float) * (size_t)B * H * W);
+    r.T = (float*)p;
     return r;
 }
+
+__device__ __forceinline__ float ce_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float CE_LOG2E = 1.4426950408889634f;
 
 // pseudo_gt float one-hot-or-empty -> uint8 labels (first maximum, like torch.argmax; 255 where the
 // pixel's sum is < 1) and per-class pixel counts.  grid (tiles_x, tiles_y, B)
@@ -67,30 +88,16 @@ labels_from_onehot_kernel(const float* __restrict__ pg, uint8_t* __restrict__ la
         label[(size_t)b * HW + i] = (uint8_t)lab;
     }
     if (count != nullptr) {
-        for (int c = 0; c < C; ++c) {  // warp-aggregated
-            const unsigned m = __ballot_sync(0xffffffffu, lab == c);
-            if (m != 0u && (threadIdx.x & 31) == 0) atomicAdd(count + (size_t)b * C + c, __popc(m));
-        }
-    }
-}
-
-// cw / bw from the counts (float arithmetic as in the reference) and zero the accumulators.  one block
-__global__ void ce_stats_kernel(const int* __restrict__ count, const float* __restrict__ gt_labels,
-                                float* __restrict__ cwbw, double* __restrict__ acc, int B, int C) {
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        float tot = 0.f;
-        int present = 0;
-        for (int c = 0; c < C; ++c) {
-            const int n = count[(size_t)b * C + c];
-            tot = __fadd_rn(tot, (float)n);
-            present += n > 0;
-        }
-        for (int c = 0; c < C; ++c)
-            cwbw[(size_t)b * (C + 1) + c] = __fdiv_rn(__fsub_rn(tot, (float)count[(size_t)b * C + c]), __fadd_rn(1.f, tot));
-        float gsum = 1.f;  // + BG
-        for (int c = 0; c < C - 1; ++c) gsum = __fadd_rn(gsum, gt_labels[(size_t)b * (C - 1) + c]);
-        cwbw[(size_t)b * (C + 1) + C] = (gsum == (float)present) ? 1.f : 0.f;
-        acc[b] = 0.0;
+        // histogram of the block in shared memory (one shared-memory atomic per distinct label of a warp), then one
+        // global atomic per class the block has seen
+        __shared__ int hist[256];
+        const int tid = threadIdx.y * LS_BX + threadIdx.x;
+        hist[tid] = 0;  // LS_BX * LS_BY == 256
+        __syncthreads();
+        const unsigned peers = __match_any_sync(0xffffffffu, lab);
+        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1 && lab < C) atomicAdd(&hist[lab], __popc(peers));
+        __syncthreads();
+        if (tid < C && hist[tid] != 0) atomicAdd(count + (size_t)b * C + tid, hist[tid]);
     }
 }
 
@@ -99,14 +106,30 @@ __device__ __forceinline__ float logit_at(const float* __restrict__ pl, int w, s
     return kResize ? bilerp(pl, w, ly, lx) : __ldg(pl + i);
 }
 
+constexpr int CE_MAXC_SMEM = 256;  // labels are uint8: C <= 255
+
 // grid (tiles_x, tiles_y, B)
 template <bool kResize>
 __global__ void __launch_bounds__(LS_BX * LS_BY)
-ce_forward_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ label, const float* __restrict__ cwbw,
-                  double* __restrict__ acc, float* __restrict__ lse_out, float* __restrict__ coef_out, int C, int h, int w,
-                  int H, int W, float sh, float sw) {
+ce_forward_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ label, const int* __restrict__ count,
+                  const float* __restrict__ gt_labels, double* __restrict__ acc, unsigned* __restrict__ ticket,
+                  float* __restrict__ bw_out, float* __restrict__ loss, float* __restrict__ lse_out,
+                  float* __restrict__ coef_out, int C, int h, int w, int H, int W, float sh, float sw, double inv_hw) {
     const int x = blockIdx.x * LS_BX + threadIdx.x, y = blockIdx.y * LS_BY + threadIdx.y, b = blockIdx.z;
     const size_t HW = (size_t)H * W, hw = (size_t)h * w, i = (size_t)y * W + x;
+    // class weights of this image (SoftMaxAE.py:71-74), float arithmetic as in the reference
+    __shared__ float s_cw[CE_MAXC_SMEM];
+    __shared__ float s_tot;
+    const int tid = threadIdx.y * LS_BX + threadIdx.x;
+    if (tid == 0) {
+        float tot = 0.f;
+        for (int c = 0; c < C; ++c) tot = __fadd_rn(tot, (float)count[(size_t)b * C + c]);
+        s_tot = tot;
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += LS_BX * LS_BY)
+        s_cw[c] = __fdiv_rn(__fsub_rn(s_tot, (float)count[(size_t)b * C + c]), __fadd_rn(1.f, s_tot));
+    __syncthreads();
     double term = 0.0;
     if (x < W && y < H) {
         const int lab = label[(size_t)b * HW + i];
@@ -114,52 +137,85 @@ ce_forward_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ 
         if (lab < C) {
             const Lerp ly = make_lerp(y, sh, h), lx = make_lerp(x, sw, w);
             const float* __restrict__ base = logits + (size_t)b * C * hw;
-            float m = -INFINITY, s = 0.f, zl = 0.f;  // online log-sum-exp
-            // classes in batches of CE_BATCH: the loads of a batch are issued before the dependent exp chain
+            float m = -INFINITY, s = 0.f, zl = 0.f;  // online log-sum-exp, base 2: s = sum 2^((z - m) log2 e)
+            // classes in batches of CE_BATCH: the loads of a batch are issued before the dependent chain
             for (int c0 = 0; c0 < C; c0 += CE_BATCH) {
                 float vb[CE_BATCH];
 #pragma unroll
                 for (int j = 0; j < CE_BATCH; ++j)
                     vb[j] = logit_at<kResize>(base + (size_t)min(c0 + j, C - 1) * hw, w, i, ly, lx);
+                float bm = vb[0];
+#pragma unroll
+                for (int j = 1; j < CE_BATCH; ++j) bm = fmaxf(bm, (c0 + j < C) ? vb[j] : vb[0]);
+                if (bm > m) {  // one rescale per batch
+                    s *= ce_ex2((m - bm) * CE_LOG2E);
+                    m = bm;
+                }
 #pragma unroll
                 for (int j = 0; j < CE_BATCH; ++j) {
                     const int c = c0 + j;
                     if (c < C) {
-                        const float v = vb[j];
-                        if (c == lab) zl = v;
-                        if (v > m) {
-                            s = s * expf(m - v) + 1.f;
-                            m = v;
-                        } else {
-                            s += expf(v - m);
-                        }
+                        if (c == lab) zl = vb[j];
+                        s += ce_ex2((vb[j] - m) * CE_LOG2E);
                     }
                 }
             }
             lse = m + logf(s);
-            const float cw = cwbw[(size_t)b * (C + 1) + lab];
+            const float cw = s_cw[lab];
             term = (double)cw * (double)(lse - zl);
             coef = cw / (float)HW;
         }
         lse_out[(size_t)b * HW + i] = lse;
         coef_out[(size_t)b * HW + i] = coef;
     }
-    // block sum in double -> one atomic per block
+    // block sum in double -> one atomic per block; the image's last block finishes the loss
     for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
     __shared__ double red[LS_BY];
     if (threadIdx.x == 0) red[threadIdx.y] = term;
     __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
+    if (tid == 0) {
         double t = 0.0;
         for (int k = 0; k < LS_BY; ++k) t += red[k];
         if (t != 0.0) atomicAdd(acc + b, t);
+        __threadfence();
+        const unsigned done = atomicAdd(ticket + b, 1u) + 1u;
+        if (done == gridDim.x * gridDim.y) {
+            __threadfence();
+            const double total = atomicAdd(acc + b, 0.0);  // every block's sum is in
+            int present = 0;
+            for (int c = 0; c < C; ++c) present += count[(size_t)b * C + c] > 0;
+            float gsum = 1.f;  // + BG (SoftMaxAE.py:82-84)
+            for (int c = 0; c < C - 1; ++c) gsum = __fadd_rn(gsum, gt_labels[(size_t)b * (C - 1) + c]);
+            const float bw = (gsum == (float)present) ? 1.f : 0.f;
+            bw_out[b] = bw;
+            loss[b] = bw * (float)(total * inv_hw);
+        }
     }
 }
 
-__global__ void ce_finalize_kernel(const double* __restrict__ acc, const float* __restrict__ cwbw, float* __restrict__ loss,
-                                   int B, int C, double inv_hw) {
-    for (int b = threadIdx.x; b < B; b += blockDim.x)
-        loss[b] = cwbw[(size_t)b * (C + 1) + C] * (float)(acc[b] * inv_hw);
+// Backward without resampling: one thread per pixel.  grid (tiles_x, tiles_y, B)
+__global__ void __launch_bounds__(LS_BX * LS_BY)
+ce_backward_same_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ label, const float* __restrict__ bw,
+                        const float* __restrict__ lse_in, const float* __restrict__ coef_in, const float* __restrict__ gout,
+                        float* __restrict__ grad, int C, int H, int W) {
+    const int x = blockIdx.x * LS_BX + threadIdx.x, y = blockIdx.y * LS_BY + threadIdx.y, b = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const size_t HW = (size_t)H * W, i = (size_t)y * W + x, p = (size_t)b * HW + i;
+    const float gc = gout[b] * bw[b] * __ldg(coef_in + p);
+    const float nl = -__ldg(lse_in + p) * CE_LOG2E;
+    const int lab = label[p];
+    const float* __restrict__ zb = logits + (size_t)b * C * HW + i;
+    float* __restrict__ gb = grad + (size_t)b * C * HW + i;
+    for (int c0 = 0; c0 < C; c0 += CE_BATCH) {
+        float vb[CE_BATCH];
+#pragma unroll
+        for (int j = 0; j < CE_BATCH; ++j) vb[j] = __ldg(zb + (size_t)min(c0 + j, C - 1) * HW);
+#pragma unroll
+        for (int j = 0; j < CE_BATCH; ++j) {
+            const int c = c0 + j;
+            if (c < C) gb[(size_t)c * HW] = (gc == 0.f) ? 0.f : gc * (ce_ex2(fmaf(vb[j], CE_LOG2E, nl)) - (c == lab ? 1.f : 0.f));
+        }
+    }
 }
 
 // Destination index range [lo, hi] whose interpolation can touch source index i (conservative; the
@@ -173,48 +229,82 @@ __device__ __forceinline__ float weight_to(const Lerp& l, int i) {
     return (l.i0 == i ? l.l0 : 0.f) + (l.i1 == i ? l.l1 : 0.f);
 }
 
-// grid (ceil(w/32), ceil(h/8), B*C): one thread per logit element.  With lse(px) stored by the forward
-// pass, class c needs only its own interpolated logit: softmax_c = exp(z_c - lse).
-template <bool kResize>
+// Backward with resampling, x pass: T[b,c,y,j].  grid (ceil(w/32), ceil(H/8), B * ceil(C/CE_BATCH)): a thread takes
+// CE_BATCH classes of one (y, j), so that what does not depend on the class (the pixel's interpolation weights, coef,
+// lse, label) is computed once per pixel for all of them.  Per class it holds r[k] = the logit column j-1+k
+// interpolated in y (k = 0..2); a pixel of the footprint then needs one FMA pair for its interpolated logit.
 __global__ void __launch_bounds__(LS_BX * LS_BY)
-ce_backward_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ label, const float* __restrict__ cwbw,
-                   const float* __restrict__ lse_in, const float* __restrict__ coef_in, const float* __restrict__ gout,
-                   float* __restrict__ grad, int C, int h, int w, int H, int W, float sh, float sw) {
-    const int j = blockIdx.x * LS_BX + threadIdx.x, i = blockIdx.y * LS_BY + threadIdx.y;
-    const int plane = blockIdx.z, b = plane / C, c = plane - b * C;
-    if (j >= w || i >= h) return;
+ce_backward_xpass_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ label, const float* __restrict__ lse_in,
+                         const float* __restrict__ coef_in, float* __restrict__ T, int C, int h, int w, int H, int W, float sh,
+                         float sw) {
+    const int j = blockIdx.x * LS_BX + threadIdx.x, y = blockIdx.y * LS_BY + threadIdx.y;
+    const int nbatch = (C + CE_BATCH - 1) / CE_BATCH;
+    const int b = blockIdx.z / nbatch, c0 = (blockIdx.z - b * nbatch) * CE_BATCH;
+    if (j >= w || y >= H) return;
     const size_t HW = (size_t)H * W, hw = (size_t)h * w;
-    const float g = gout[b] * cwbw[(size_t)b * (C + 1) + C];
-    float acc = 0.f;
-    if (g != 0.f) {
-        const float* __restrict__ pl = logits + (size_t)plane * hw;
-        int ylo = i, yhi = i, xlo = j, xhi = j;
-        if (kResize) {
-            footprint(i, sh, H, ylo, yhi);
-            footprint(j, sw, W, xlo, xhi);
-        }
-        for (int y = ylo; y <= yhi; ++y) {
-            const Lerp ly = make_lerp(y, sh, h);
-            const float wy = kResize ? weight_to(ly, i) : 1.f;
-            if (wy == 0.f) continue;
-            for (int x = xlo; x <= xhi; ++x) {
-                const Lerp lx = make_lerp(x, sw, w);
-                const float wx = kResize ? weight_to(lx, j) : 1.f;
-                const size_t pi = (size_t)y * W + x, p = (size_t)b * HW + pi;
-                const float coef = __ldg(coef_in + p);
-                if (wx == 0.f || coef == 0.f) continue;
-                const float z = logit_at<kResize>(pl, w, pi, ly, lx);
-                acc = fmaf(coef * wy * wx, expf(z - __ldg(lse_in + p)) - (label[p] == c ? 1.f : 0.f), acc);
-            }
+    const Lerp ly = make_lerp(y, sh, h);
+    const int jm = max(j - 1, 0), jp = min(j + 1, w - 1);
+    float r[CE_BATCH][3], acc[CE_BATCH];
+#pragma unroll
+    for (int q = 0; q < CE_BATCH; ++q) {
+        const float* __restrict__ pl = logits + ((size_t)b * C + min(c0 + q, C - 1)) * hw;
+        const float* __restrict__ p0 = pl + (size_t)ly.i0 * w;
+        const float* __restrict__ p1 = pl + (size_t)ly.i1 * w;
+        r[q][0] = fmaf(ly.l1, __ldg(p1 + jm), ly.l0 * __ldg(p0 + jm));
+        r[q][1] = fmaf(ly.l1, __ldg(p1 + j), ly.l0 * __ldg(p0 + j));
+        r[q][2] = fmaf(ly.l1, __ldg(p1 + jp), ly.l0 * __ldg(p0 + jp));
+        acc[q] = 0.f;
+    }
+    int xlo, xhi;
+    footprint(j, sw, W, xlo, xhi);
+    const size_t row = (size_t)b * HW + (size_t)y * W;
+    for (int x = xlo; x <= xhi; ++x) {
+        const Lerp lx = make_lerp(x, sw, w);
+        const float wx = weight_to(lx, j);
+        const float cwx = __ldg(coef_in + row + x) * wx;
+        if (cwx == 0.f) continue;
+        const float nl = -__ldg(lse_in + row + x) * CE_LOG2E;
+        const int lab = (int)label[row + x] - c0;
+        // lx.i0 is j-1 or j; lx.i1 is lx.i0 + 1, or lx.i0 on the last column (where r[.][2] == r[.][1] already)
+        const bool left = lx.i0 < j;
+#pragma unroll
+        for (int q = 0; q < CE_BATCH; ++q) {
+            const float z = fmaf(lx.l1, left ? r[q][1] : r[q][2], lx.l0 * (left ? r[q][0] : r[q][1]));
+            acc[q] = fmaf(cwx, ce_ex2(fmaf(z, CE_LOG2E, nl)) - (lab == q ? 1.f : 0.f), acc[q]);
         }
     }
-    grad[(size_t)plane * hw + (size_t)i * w + j] = g * acc;
+#pragma unroll
+    for (int q = 0; q < CE_BATCH; ++q)
+        if (c0 + q < C) T[(((size_t)b * C + c0 + q) * H + y) * w + j] = acc[q];
+}
+
+// y pass: grad[b,c,i,j] = g_b * bw_b * sum_y T[b,c,y,j] * wy(y -> i).  grid (ceil(w/32), ceil(h/8), B*C)
+__global__ void __launch_bounds__(LS_BX * LS_BY)
+ce_backward_ypass_kernel(const float* __restrict__ T, const float* __restrict__ bw, const float* __restrict__ gout,
+                         float* __restrict__ grad, int C, int h, int w, int H, float sh) {
+    const int j = blockIdx.x * LS_BX + threadIdx.x, i = blockIdx.y * LS_BY + threadIdx.y;
+    const int plane = blockIdx.z, b = plane / C;
+    if (j >= w || i >= h) return;
+    const float g = gout[b] * bw[b];
+    float acc = 0.f;
+    if (g != 0.f) {
+        int ylo, yhi;
+        footprint(i, sh, H, ylo, yhi);
+        const float* __restrict__ tp = T + (size_t)plane * H * w + j;
+        for (int y = ylo; y <= yhi; ++y) {
+            const float wy = weight_to(make_lerp(y, sh, h), i);
+            if (wy != 0.f) acc = fmaf(wy, __ldg(tp + (size_t)y * w), acc);
+        }
+    }
+    grad[(size_t)plane * h * w + (size_t)i * w + j] = g * acc;
 }
 
 }  // namespace
 
-size_t mask_ce_workspace_bytes(int B, int C, int H, int W) {
-    return up256(sizeof(double) * B) + up256(sizeof(float) * (size_t)B * (C + 1)) + 2 * up256(sizeof(float) * (size_t)B * H * W);
+size_t mask_ce_workspace_bytes(int B, int C, int h, int w, int H, int W) {
+    const size_t t_bytes = (h != H || w != W) ? up256(sizeof(float) * (size_t)B * C * H * w) : 0;
+    return up256(sizeof(double) * B) + up256(sizeof(unsigned) * B) + up256(sizeof(float) * B) +
+           2 * up256(sizeof(float) * (size_t)B * H * W) + t_bytes;
 }
 
 int launch_labels_from_onehot(const float* pseudo_gt, uint8_t* label, int* class_count, int B, int C, int H, int W,
@@ -231,24 +321,21 @@ int launch_labels_from_onehot(const float* pseudo_gt, uint8_t* label, int* class
 int launch_mask_ce_forward(const float* logits, const uint8_t* label, const int* class_count, const float* gt_labels,
                            float* loss, void* ws, size_t ws_bytes, int B, int C, int h, int w, int H, int W,
                            cudaStream_t s) {
-    if (ws == nullptr || ws_bytes < mask_ce_workspace_bytes(B, C, H, W))
+    if (ws == nullptr || ws_bytes < mask_ce_workspace_bytes(B, C, h, w, H, W))
         return set_error(PAMR_ERR_WORKSPACE, "mask_ce: workspace of %zu bytes given, %zu needed", ws_bytes,
-                         mask_ce_workspace_bytes(B, C, H, W));
+                         mask_ce_workspace_bytes(B, C, h, w, H, W));
     if (((uintptr_t)ws & 255) != 0) return set_error(PAMR_ERR_INVALID_ARGUMENT, "mask_ce: workspace must be 256-byte aligned");
-    const CeWorkspace k = carve(ws, B, C, H, W);
-    ce_stats_kernel<<<1, 128, 0, s>>>(class_count, gt_labels, k.cwbw, k.acc, B, C);
-    count_launch();
-    PAMR_CUDA_TRY(cudaGetLastError());
+    if (C >= CE_MAXC_SMEM) return set_error(PAMR_ERR_INVALID_ARGUMENT, "mask_ce: C=%d does not fit a uint8 label map", C);
+    const CeWorkspace k = carve(ws, B, H, W);
+    PAMR_CUDA_TRY(cudaMemsetAsync(k.acc, 0, k.head_bytes, s));  // accumulators and tickets
     dim3 grid((W + LS_BX - 1) / LS_BX, (H + LS_BY - 1) / LS_BY, B), block(LS_BX, LS_BY);
     if (grid.y > 65535 || grid.z > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "mask_ce: H/8 and B must be <= 65535");
     const float sh = scale_of(h, H), sw = scale_of(w, W);
+    const double inv_hw = 1.0 / ((double)H * (double)W);
     if (h != H || w != W)
-        ce_forward_kernel<true><<<grid, block, 0, s>>>(logits, label, k.cwbw, k.acc, k.lse, k.coef, C, h, w, H, W, sh, sw);
+        ce_forward_kernel<true><<<grid, block, 0, s>>>(logits, label, class_count, gt_labels, k.acc, k.ticket, k.bw, loss, k.lse, k.coef, C, h, w, H, W, sh, sw, inv_hw);
     else
-        ce_forward_kernel<false><<<grid, block, 0, s>>>(logits, label, k.cwbw, k.acc, k.lse, k.coef, C, h, w, H, W, sh, sw);
-    count_launch();
-    PAMR_CUDA_TRY(cudaGetLastError());
-    ce_finalize_kernel<<<1, 128, 0, s>>>(k.acc, k.cwbw, loss, B, C, 1.0 / ((double)H * (double)W));
+        ce_forward_kernel<false><<<grid, block, 0, s>>>(logits, label, class_count, gt_labels, k.acc, k.ticket, k.bw, loss, k.lse, k.coef, C, h, w, H, W, sh, sw, inv_hw);
     count_launch();
     PAMR_CUDA_TRY(cudaGetLastError());
     return PAMR_OK;
@@ -256,17 +343,28 @@ int launch_mask_ce_forward(const float* logits, const uint8_t* label, const int*
 
 int launch_mask_ce_backward(const float* logits, const uint8_t* label, const float* grad_loss, float* grad_logits,
                             const void* ws, size_t ws_bytes, int B, int C, int h, int w, int H, int W, cudaStream_t s) {
-    if (ws == nullptr || ws_bytes < mask_ce_workspace_bytes(B, C, H, W))
+    if (ws == nullptr || ws_bytes < mask_ce_workspace_bytes(B, C, h, w, H, W))
         return set_error(PAMR_ERR_WORKSPACE, "mask_ce backward: workspace of %zu bytes given, %zu needed", ws_bytes,
-                         mask_ce_workspace_bytes(B, C, H, W));
-    const CeWorkspace k = carve(const_cast<void*>(ws), B, C, H, W);
-    dim3 grid((w + LS_BX - 1) / LS_BX, (h + LS_BY - 1) / LS_BY, B * C), block(LS_BX, LS_BY);
-    if (grid.y > 65535 || grid.z > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "mask_ce backward: h/8 and B*C must be <= 65535");
+                         mask_ce_workspace_bytes(B, C, h, w, H, W));
+    const CeWorkspace k = carve(const_cast<void*>(ws), B, H, W);
+    dim3 block(LS_BX, LS_BY);
+    if (h == H && w == W) {
+        dim3 grid((W + LS_BX - 1) / LS_BX, (H + LS_BY - 1) / LS_BY, B);
+        if (grid.y > 65535 || grid.z > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "mask_ce backward: H/8 and B must be <= 65535");
+        ce_backward_same_kernel<<<grid, block, 0, s>>>(logits, label, k.bw, k.lse, k.coef, grad_loss, grad_logits, C, H, W);
+        count_launch();
+        PAMR_CUDA_TRY(cudaGetLastError());
+        return PAMR_OK;
+    }
     const float sh = scale_of(h, H), sw = scale_of(w, W);
-    if (h != H || w != W)
-        ce_backward_kernel<true><<<grid, block, 0, s>>>(logits, label, k.cwbw, k.lse, k.coef, grad_loss, grad_logits, C, h, w, H, W, sh, sw);
-    else
-        ce_backward_kernel<false><<<grid, block, 0, s>>>(logits, label, k.cwbw, k.lse, k.coef, grad_loss, grad_logits, C, h, w, H, W, sh, sw);
+    dim3 gx((w + LS_BX - 1) / LS_BX, (H + LS_BY - 1) / LS_BY, B * ((C + CE_BATCH - 1) / CE_BATCH));
+    dim3 gy((w + LS_BX - 1) / LS_BX, (h + LS_BY - 1) / LS_BY, B * C);
+    if (gx.y > 65535 || gy.y > 65535 || gy.z > 65535)
+        return set_error(PAMR_ERR_INVALID_ARGUMENT, "mask_ce backward: H/8, h/8 and B*C must be <= 65535");
+    ce_backward_xpass_kernel<<<gx, block, 0, s>>>(logits, label, k.lse, k.coef, k.T, C, h, w, H, W, sh, sw);
+    count_launch();
+    PAMR_CUDA_TRY(cudaGetLastError());
+    ce_backward_ypass_kernel<<<gy, block, 0, s>>>(k.T, k.bw, grad_loss, grad_logits, C, h, w, H, sh);
     count_launch();
     PAMR_CUDA_TRY(cudaGetLastError());
     return PAMR_OK;

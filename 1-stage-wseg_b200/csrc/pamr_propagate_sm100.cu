@@ -85,13 +85,19 @@ static_assert(NBAR % NSLOT == 0 && NBAR >= 2 * NSLOT, "barrier ring must cover a
 // ring), 14 and 15 weight issuers (tcgen05.cp staging -> TMEM; even / odd units).
 constexpr int W_PRODUCER = NWC, W_LOADER = NWC + 1, W_ISSUER = NWC + 2;
 constexpr int NTHREADS = (NWC + 4) * 32;
-constexpr int CHUNK_UNITS = 2;        // units handed over together ("chunk": 64 TMEM columns, 32 KB; the last chunk of a tile may be short)
+#ifndef PAMR_CHUNK_UNITS
+#define PAMR_CHUNK_UNITS 2
+#endif
+constexpr int CHUNK_UNITS = PAMR_CHUNK_UNITS;  // units handed over together ("chunk": CHUNK_UNITS x 32 TMEM columns = CHUNK_UNITS x 16 KB; the last chunk of a tile may be short)
 constexpr int NSTG = PAMR_NSTG;       // staging ring for the weights: NSTG chunks of 32 KB
 constexpr int PF_PLANES = PAMR_PF_PLANES;  // class planes pulled into L2 this many classes ahead of their TMA load (0: off)
 constexpr int WB = 16;                // weights per tcgen05.ld batch of the centre column
-constexpr int UNIT = 32;              // TMEM columns per fill unit (= 2 batches)
+#ifndef PAMR_UNIT
+#define PAMR_UNIT 32
+#endif
+constexpr int UNIT = PAMR_UNIT;       // TMEM columns per fill unit (a multiple of the 16-column batch)
 constexpr int UNIT_BYTES = UNIT * 128 * 4;  // 128 TMEM lanes
-constexpr int MAX_CHUNKS = 8;
+constexpr int MAX_CHUNKS = (480 / (CHUNK_UNITS * UNIT) + 2) / 2 * 2;  // >= chunks per tile (R = 10: 480 columns), even
 constexpr int CTRL_BYTES = 1024;
 constexpr int CS_MAX_W = 1;           // widest column strip the border tiles take on
 constexpr int RS_MAX_H = 8;           // tallest row strip
@@ -694,7 +700,11 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             const uint32_t tb = ctrl->tmem_base;
             [[maybe_unused]] int ev_n = 0;
             int n = warp - W_ISSUER;
-            static_assert(L::NCH % 2 == 0, "a chunk index must always meet the same issuer (mbarrier waits are by phase parity)");
+            // Waits are by phase parity, so a waiter must never be a whole phase early on its barrier.  With an even number
+            // of chunks per tile a chunk index always meets the same issuer; with an odd number the two issuers alternate
+            // on free_bar[c], which is still sound because the loader throttles the stream: an issuer can be at most
+            // NSTG chunks ahead of the other one, i.e. less than a tile (NCH chunks) apart.
+            static_assert(L::NCH % 2 == 0 || NSTG < L::NCH, "the issuers must stay less than a tile apart");
             if (n < total) mbar_wait(smem_u32(&ctrl->staged_bar[n % (2 * NSTG)]), (uint32_t)(n / (2 * NSTG)) & 1u);  // bytes landed
             int cs_uses = 0;  // border tiles of this CTA so far
             for (; n < total; n += 2) {

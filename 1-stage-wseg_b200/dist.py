@@ -110,16 +110,24 @@ class OverlappedLabelGather:
         if not self.cuda:
             dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
             if host_out is not None:
-                host_out.copy_(out)
+                host_out.copy_(self._host_view(out, local, host_out))
             return out
         main = torch.cuda.current_stream(self.device)
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             dist.all_gather_into_tensor(out, local, group=self.group)
             if host_out is not None:
-                host_out.copy_(out, non_blocking=True)
+                host_out.copy_(self._host_view(out, local, host_out), non_blocking=True)
         local.record_stream(self.side)  # the allocator must not hand `local` out again before the gather has read it
         return out
+
+    def _host_view(self, out, local, host_out):
+        if host_out.shape[0] == out.shape[0]:
+            return out
+        b, rank = local.shape[0], dist.get_rank(self.group)
+        if host_out.shape[0] != b:
+            raise RuntimeError("host_out must hold all %d gathered maps or this rank's %d" % (out.shape[0], b))
+        return out[rank * b: (rank + 1) * b]
 
     def wait(self):
         """Everything submitted so far becomes visible to the caller's current stream."""

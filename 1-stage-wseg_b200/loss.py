@@ -22,7 +22,7 @@ class _MaskCE(torch.autograd.Function):
         B, C, h, w = logits.shape
         H, W = int(label.shape[-2]), int(label.shape[-1])
         L = _lib.lib()
-        need = L.pamr_mask_ce_workspace_bytes(B, C, H, W)
+        need = L.pamr_mask_ce_workspace_bytes(B, C, h, w, H, W)
         ws = torch.empty((need,), dtype=torch.uint8, device=logits.device)
         loss = torch.empty((B,), dtype=torch.float32, device=logits.device)
         _lib.check(L.pamr_mask_ce_forward_f32(logits.data_ptr(), label.data_ptr(), counts.data_ptr(), gt_labels.data_ptr(),

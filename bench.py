@@ -334,13 +334,14 @@ def main():
     pipe = wseg_b200.HostPipeline(pamr, dev, chunks=int(os.environ.get("PAMR_BENCH_CHUNKS", "1")))
 
     def e2e_record(h_image, h_mask, h_labels):
-        h_out = torch.empty((world * B if world > 1 else B, H, W), dtype=torch.uint8).pin_memory()
+        # every rank reads back its own shard of the (gathered) label maps: each map reaches the host once per step
+        h_out = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
         d_local = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
 
         def e2e_step():
             if world == 1:
                 pipe(h_image, h_mask, h_labels, h_out, out_size=(H, W))
-            else:  # per-rank shard through the pipeline, the NCCL gather of the labels and the D2H on the side stream
+            else:  # per-rank shard through the pipeline; the NCCL gather of the labels and the D2H of the own slice on the side stream
                 pipe(h_image, h_mask, h_labels, d_out=d_local, out_size=(H, W))
                 gather.submit(d_local, host_out=h_out)
 

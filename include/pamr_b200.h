@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PAMR_B200_ABI_VERSION 1
+#define PAMR_B200_ABI_VERSION 2
 
 #define PAMR_OK 0
 #define PAMR_ERR_INVALID_ARGUMENT 1
@@ -151,13 +151,13 @@ int pamr_pseudo_labels_f32(const float* m, const float* labels, const unsigned* 
  * SoftMaxAE.py:58) to the label resolution [H,W];
  *   cw[b,c] = (tot_b - n[b,c]) / (1 + tot_b)   bw[b] = (sum_c gt_labels[b,c] + 1 == #{c: n[b,c] > 0})
  *   loss[b] = bw[b] * (1/(H*W)) * sum_px cw[b,label] * (logsumexp_c z - z[label])      (ignored pixels add 0)
- * The workspace (pamr_mask_ce_workspace_bytes, 256-byte aligned) keeps per-pixel log-sum-exp and weights
- * for the backward call.
+ * The workspace (pamr_mask_ce_workspace_bytes for the same B, C, h, w, H, W; 256-byte aligned) keeps per-pixel
+ * log-sum-exp and weights for the backward call, and the backward call's intermediate when (h,w) != (H,W).
  *
  * pamr_mask_ce_backward_f32: grad_logits [B,C,h,w] = d(sum_b grad_loss[b]*loss[b]) / d logits, from the
  * same logits / label map and the workspace the forward call filled.  Deterministic (gather, no atomics).
  */
-size_t pamr_mask_ce_workspace_bytes(int B, int C, int H, int W);
+size_t pamr_mask_ce_workspace_bytes(int B, int C, int h, int w, int H, int W);
 int pamr_labels_from_onehot_f32(const float* pseudo_gt, uint8_t* label, int* class_count, int B, int C, int H, int W,
                                 int dev, pamr_stream_t stream);
 int pamr_mask_ce_forward_f32(const float* logits, const uint8_t* label, const int* class_count, const float* gt_labels,

@@ -184,7 +184,11 @@ def _overlapped_gather_worker(rank, world, port, q):
             outs.append((out, full))
             if len(outs) >= 2:
                 ok = ok and bool(torch.equal(outs[-2][0], outs[-2][1]))  # the previous step's buffer is still intact
-        ok = ok and outs[-1][0].data_ptr() == outs[-3][0].data_ptr() != outs[-2][0].data_ptr()
+        ok = ok and len({o.data_ptr() for o, _ in outs}) == 2  # two rotating output buffers
+        own = torch.empty((2, 3, 4), dtype=torch.uint8)
+        g.submit(full[2 * rank: 2 * rank + 2].clone(), host_out=own)  # [b,...]: this rank's slice of the gathered buffer
+        g.wait()
+        ok = ok and bool(torch.equal(own, full[2 * rank: 2 * rank + 2]))
         # a rank with an empty shard (B < world) still takes part in the gather of ShardedPseudoLabeler
         empty = wseg_b200.gather_labels(torch.full((1 if rank == 0 else 0, 2, 2), 9, dtype=torch.uint8), 1)
         ok = ok and tuple(empty.shape) == (1, 2, 2) and int(empty.sum()) == 36

@@ -62,6 +62,14 @@ constexpr int NW = 4;                 // warps per compute group (= TMEM lane qu
 #define PAMR_NG 3
 #endif
 constexpr int NG = PAMR_NG;           // compute groups that share the tile's weights in TMEM (class c -> group c % NG)
+// Classes per pass.  2: a group takes two class planes per pass and applies every weight it has fetched from Tensor
+// Memory to both, which halves the Tensor-Memory read traffic per pixel-class -- tcgen05.ld and LDS share the path
+// back into the register file, and that path (~205 B/clk/SM for this mix, profiles/r01_ubench_tmem.txt), not either
+// pipe alone, is what bounds the one-class kernel.
+#ifndef PAMR_CPP
+#define PAMR_CPP 1
+#endif
+constexpr int CPP = PAMR_CPP;
 constexpr int NWC = NG * NW;          // compute warps
 #ifndef PAMR_NSLOT
 #define PAMR_NSLOT 4
@@ -167,6 +175,41 @@ __device__ __forceinline__ void tmem_wait_ld(float (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
                    "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]));
+}
+// 32 / 8 / 4 consecutive columns (two-classes-per-pass kernel: one load per tap segment)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
+          "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]),
+          "=f"(r[17]), "=f"(r[18]), "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]),
+          "=f"(r[25]), "=f"(r[26]), "=f"(r[27]), "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16p(uint32_t taddr, float* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]),
+          "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8p(uint32_t taddr, float* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4p(uint32_t taddr, float* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3])
+                 : "r"(taddr));
+}
+// tcgen05.wait::ld with a 32-register segment buffer tied through the asm
+__device__ __forceinline__ void tmem_wait_ld32(float* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
+                   "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]),
+                   "+f"(r[16]), "+f"(r[17]), "+f"(r[18]), "+f"(r[19]), "+f"(r[20]), "+f"(r[21]), "+f"(r[22]), "+f"(r[23]),
+                   "+f"(r[24]), "+f"(r[25]), "+f"(r[26]), "+f"(r[27]), "+f"(r[28]), "+f"(r[29]), "+f"(r[30]), "+f"(r[31]));
 }
 // plain bulk copy global -> shared memory, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -432,6 +475,220 @@ __device__ __forceinline__ void compute_pass(const float* __restrict__ sp, uint3
 #undef PAMR_ENTER_BATCH
 }
 
+// ---- two classes per pass (CPP == 2) ----
+// The 48 taps are walked in 18 SEGMENTS of weights that share one register strip of class-plane rows: 6 for the
+// centre column (dilation id: taps dy = -d, +d; 2R TMEM columns) and 12 for the side columns ((bi, id): taps
+// dy = -d, 0, +d at dx = -+d; 3R columns).  A segment's weights are fetched from Tensor Memory ONCE (double
+// buffered: the next segment's load is in flight while this one is used) and applied first to plane 0, then to
+// plane 1; the strip registers are reused between the planes.  Tap-sequence order is unchanged, so every pixel's 48
+// products are still added in the same order as on every other path.
+// (Unlike the one-class pass the centre column's rows are not shared between dilations: 36.4 instead of 31.8 LDS
+// words per pixel-class, against 24 + instead of 48 Tensor-Memory words.)
+template <int R>
+struct Seg {
+    // segment index s: 0..5 centre (id = s), 6..17 side (g = s - 6 = 6 bi + id)
+    __host__ __device__ static constexpr int col0(int s) { return s < 6 ? 2 * s * R : (12 + 3 * (s - 6)) * R; }
+    __host__ __device__ static constexpr int ncol(int s) { return s < 6 ? 2 * R : 3 * R; }
+};
+constexpr int CHUNK_COLS = CHUNK_UNITS * UNIT;
+
+// loads the weights of segment s into w[0 .. ncol): one or two power-of-two loads; reading a few columns past the
+// segment is harmless (they belong to the next segment of the same tile, or to spare columns)
+template <int R, int S>
+__device__ __forceinline__ void seg_load(uint32_t tbase, float* w) {
+    constexpr int c0 = Seg<R>::col0(S), n = Seg<R>::ncol(S);
+    if constexpr (n <= 16) {
+        tmem_ld16p(tbase + c0, w);
+    } else if constexpr (n <= 20) {
+        tmem_ld16p(tbase + c0, w);
+        tmem_ld4p(tbase + c0 + 16, w + 16);
+    } else if constexpr (n <= 24) {
+        tmem_ld16p(tbase + c0, w);
+        tmem_ld8p(tbase + c0 + 16, w + 16);
+    } else {
+        static_assert(n <= 32 && c0 + 32 <= 512, "segment");
+        tmem_ld32(tbase + c0, w);
+    }
+}
+
+// FMAs of one centre segment (dilation id) for one plane: rows y -+ d of the thread's own column
+template <int R, int ID>
+__device__ __forceinline__ void seg_centre_plane(const float* __restrict__ sp, const float* w, float (&acc)[R]) {
+    constexpr int d = dil_of(ID);
+    float v[R + 2 * HALO];
+#pragma unroll
+    for (int r = -HALO; r < R + HALO; r += 2) {
+        bool need = false;
+#pragma unroll
+        for (int rr = r; rr < r + 2; ++rr) need = need || (rr >= -d && rr < R - d) || (rr >= d && rr < R + d);
+        if (need) lds_pair(sp + (r / 2) * ROWP, v[r + HALO], v[r + 1 + HALO]);
+    }
+#pragma unroll
+    for (int a = -1; a <= 1; a += 2) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const bool pair = (d % 2 == 0);
+            if (pair && (i % 2 == 1)) continue;
+            const int q = (a > 0 ? R : 0) + i;
+            if (pair) fma2(acc[i], acc[i + 1], w[q], w[q + 1], v[i + a * d + HALO], v[i + 1 + a * d + HALO]);
+            else acc[i] = fmaf(w[q], v[i + a * d + HALO], acc[i]);
+        }
+    }
+}
+// FMAs of one side segment (bi, id) for one plane
+template <int R, int BI, int ID>
+__device__ __forceinline__ void seg_side_plane(const float* __restrict__ sp, const float* w, float (&acc)[R], int xg, int W) {
+    constexpr int d = dil_of(ID), sgn = BI * 2 - 1;
+    float v[R + 2 * HALO];
+    const int coff = (min(max(xg + sgn * d, 0), W - 1) - xg) * 2;
+#pragma unroll
+    for (int r = -HALO; r < R + HALO; r += 2) {
+        bool need = false;
+#pragma unroll
+        for (int rr = r; rr < r + 2; ++rr)
+            need = need || (rr >= -d && rr < R + d && ((rr < R - d) || (rr >= 0 && rr < R) || (rr >= d)));
+        if (need) lds_pair(sp + (r / 2) * ROWP + coff, v[r + HALO], v[r + 1 + HALO]);
+    }
+#pragma unroll
+    for (int a = -1; a <= 1; ++a) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const bool pair = ((a * d) % 2 == 0);
+            if (pair && (i % 2 == 1)) continue;
+            const int q = (a + 1) * R + i;
+            if (pair) fma2(acc[i], acc[i + 1], w[q], w[q + 1], v[i + a * d + HALO], v[i + 1 + a * d + HALO]);
+            else acc[i] = fmaf(w[q], v[i + a * d + HALO], acc[i]);
+        }
+    }
+}
+
+// the same for two planes at once: both strips are loaded before the first FMA and the FMAs of the two planes
+// alternate (ten independent accumulator pairs instead of five: the kernel runs only two warps per scheduler)
+template <int R, int ID>
+__device__ __forceinline__ void seg_centre_both(const float* __restrict__ sp0, const float* __restrict__ sp1, const float* w,
+                                                float (&acc0)[R], float (&acc1)[R]) {
+    constexpr int d = dil_of(ID);
+    float v0[R + 2 * HALO], v1[R + 2 * HALO];
+#pragma unroll
+    for (int r = -HALO; r < R + HALO; r += 2) {
+        bool need = false;
+#pragma unroll
+        for (int rr = r; rr < r + 2; ++rr) need = need || (rr >= -d && rr < R - d) || (rr >= d && rr < R + d);
+        if (need) {
+            lds_pair(sp0 + (r / 2) * ROWP, v0[r + HALO], v0[r + 1 + HALO]);
+            lds_pair(sp1 + (r / 2) * ROWP, v1[r + HALO], v1[r + 1 + HALO]);
+        }
+    }
+#pragma unroll
+    for (int a = -1; a <= 1; a += 2) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const bool pair = (d % 2 == 0);
+            if (pair && (i % 2 == 1)) continue;
+            const int q = (a > 0 ? R : 0) + i;
+            if (pair) {
+                fma2(acc0[i], acc0[i + 1], w[q], w[q + 1], v0[i + a * d + HALO], v0[i + 1 + a * d + HALO]);
+                fma2(acc1[i], acc1[i + 1], w[q], w[q + 1], v1[i + a * d + HALO], v1[i + 1 + a * d + HALO]);
+            } else {
+                acc0[i] = fmaf(w[q], v0[i + a * d + HALO], acc0[i]);
+                acc1[i] = fmaf(w[q], v1[i + a * d + HALO], acc1[i]);
+            }
+        }
+    }
+}
+template <int R, int BI, int ID>
+__device__ __forceinline__ void seg_side_both(const float* __restrict__ sp0, const float* __restrict__ sp1, const float* w,
+                                              float (&acc0)[R], float (&acc1)[R], int xg, int W) {
+    constexpr int d = dil_of(ID), sgn = BI * 2 - 1;
+    float v0[R + 2 * HALO], v1[R + 2 * HALO];
+    const int coff = (min(max(xg + sgn * d, 0), W - 1) - xg) * 2;
+#pragma unroll
+    for (int r = -HALO; r < R + HALO; r += 2) {
+        bool need = false;
+#pragma unroll
+        for (int rr = r; rr < r + 2; ++rr)
+            need = need || (rr >= -d && rr < R + d && ((rr < R - d) || (rr >= 0 && rr < R) || (rr >= d)));
+        if (need) {
+            lds_pair(sp0 + (r / 2) * ROWP + coff, v0[r + HALO], v0[r + 1 + HALO]);
+            lds_pair(sp1 + (r / 2) * ROWP + coff, v1[r + HALO], v1[r + 1 + HALO]);
+        }
+    }
+#pragma unroll
+    for (int a = -1; a <= 1; ++a) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const bool pair = ((a * d) % 2 == 0);
+            if (pair && (i % 2 == 1)) continue;
+            const int q = (a + 1) * R + i;
+            if (pair) {
+                fma2(acc0[i], acc0[i + 1], w[q], w[q + 1], v0[i + a * d + HALO], v0[i + 1 + a * d + HALO]);
+                fma2(acc1[i], acc1[i + 1], w[q], w[q + 1], v1[i + a * d + HALO], v1[i + 1 + a * d + HALO]);
+            } else {
+                acc0[i] = fmaf(w[q], v0[i + a * d + HALO], acc0[i]);
+                acc1[i] = fmaf(w[q], v1[i + a * d + HALO], acc1[i]);
+            }
+        }
+    }
+}
+
+// entering segment S (its load was issued during segment S-1): wait for it, release the chunks it completes (last
+// pass of the tile), issue the load of segment S+1 (first pass of the tile: once its chunks are filled)
+template <int R, int S>
+__device__ __forceinline__ void seg_enter(uint32_t tbase, float* wcur, float* wnext, uint32_t filled_bar, uint32_t free_bar,
+                                          uint32_t par, int lane) {
+    using L = TmemLayout<R>;
+    tmem_wait_ld32(wcur);
+    if (free_bar) {
+        // chunks whose last column has now been read: [first chunk not released by segment S-1, last chunk fully inside columns < end(S))
+        constexpr int end_prev = S == 0 ? 0 : Seg<R>::col0(S - 1) + Seg<R>::ncol(S - 1);
+        constexpr int end_cur = Seg<R>::col0(S) + Seg<R>::ncol(S);
+        constexpr int lo = end_prev / CHUNK_COLS;                                   // chunks [0, lo) were released before
+        constexpr int hi = (S == 17) ? L::NCH : end_cur / CHUNK_COLS;               // chunks [lo, hi) are complete now
+#pragma unroll
+        for (int c = lo; c < hi; ++c) signal_free(free_bar + 8 * c, lane);
+    }
+    if constexpr (S + 1 < 18) {
+        if (filled_bar) {
+            // the next segment reads columns [col0, col0 + ncol): wait for the chunks it touches that no earlier segment waited for
+            constexpr int end_cur = Seg<R>::col0(S) + Seg<R>::ncol(S);
+            constexpr int end_next = Seg<R>::col0(S + 1) + Seg<R>::ncol(S + 1);
+            constexpr int lo = (end_cur - 1) / CHUNK_COLS + 1;
+            constexpr int hi = (end_next - 1) / CHUNK_COLS;
+#pragma unroll
+            for (int c = lo; c <= hi; ++c) mbar_wait(filled_bar + 8 * c, par);
+            if (lo <= hi) tc_fence_after();
+        }
+        seg_load<R, S + 1>(tbase, wnext);
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void compute_pass2(const float* __restrict__ sp0, const float* __restrict__ sp1, bool two, uint32_t tbase,
+                                              float (&acc0)[R], float (&acc1)[R], int xg, int W, uint32_t filled_bar,
+                                              uint32_t free_bar, uint32_t par, int lane) {
+    float wa[32], wb[32];
+    if (filled_bar) {
+        constexpr int hi = (Seg<R>::col0(0) + Seg<R>::ncol(0) - 1) / CHUNK_COLS;
+#pragma unroll
+        for (int c = 0; c <= hi; ++c) mbar_wait(filled_bar + 8 * c, par);
+        tc_fence_after();
+    }
+    seg_load<R, 0>(tbase, wa);
+#define PAMR_CENTRE(S, WC, WN)                                                    \
+    seg_enter<R, S>(tbase, WC, WN, filled_bar, free_bar, par, lane);              \
+    if (two) seg_centre_both<R, S>(sp0, sp1, WC, acc0, acc1);                     \
+    else seg_centre_plane<R, S>(sp0, WC, acc0);
+#define PAMR_SIDE(S, WC, WN)                                                      \
+    seg_enter<R, S>(tbase, WC, WN, filled_bar, free_bar, par, lane);              \
+    if (two) seg_side_both<R, ((S) - 6) / 6, ((S) - 6) % 6>(sp0, sp1, WC, acc0, acc1, xg, W); \
+    else seg_side_plane<R, ((S) - 6) / 6, ((S) - 6) % 6>(sp0, WC, acc0, xg, W);
+    PAMR_CENTRE(0, wa, wb) PAMR_CENTRE(1, wb, wa) PAMR_CENTRE(2, wa, wb) PAMR_CENTRE(3, wb, wa) PAMR_CENTRE(4, wa, wb) PAMR_CENTRE(5, wb, wa)
+    PAMR_SIDE(6, wa, wb) PAMR_SIDE(7, wb, wa) PAMR_SIDE(8, wa, wb) PAMR_SIDE(9, wb, wa) PAMR_SIDE(10, wa, wb) PAMR_SIDE(11, wb, wa)
+    PAMR_SIDE(12, wa, wb) PAMR_SIDE(13, wb, wa) PAMR_SIDE(14, wa, wb) PAMR_SIDE(15, wb, wa) PAMR_SIDE(16, wa, wb) PAMR_SIDE(17, wb, wa)
+#undef PAMR_CENTRE
+#undef PAMR_SIDE
+}
+
 template <int R>
 __device__ __forceinline__ bool needs_patch(int y0, int H) {
     // replicate padding in x is handled by the per-lane column offsets
@@ -577,7 +834,8 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem_raw + C_::CTRL_OFF);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int C = prm.C, H = prm.H, W = prm.W;
-    const int active_groups = C < NG ? C : NG;  // groups that have at least one class pass per tile
+    const int npass_units = (C + CPP - 1) / CPP;                      // class passes per tile
+    const int active_groups = npass_units < NG ? npass_units : NG;  // groups that have at least one class pass per tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NBAR; ++s) {
@@ -753,13 +1011,106 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             const bool border = needs_patch<R>(y0, H);
             const int nrow = xok ? max(0, min(R, H - yw)) : 0;  // rows of this thread inside the image
             const bool cs_tile = wc > 0 && (t % prm.tiles_x == prm.tiles_x - 1);  // this tile also computes the column strip
-            if (cs_tile && grp < C) {
+            if (cs_tile && grp < active_groups) {
                 mbar_wait(smem_u32(&ctrl->csw_full_bar), (uint32_t)cs_seen & 1u);  // its strip weights are in TMEM
                 tc_fence_after();
                 ++cs_seen;
             }
 
+            // ---- store of one class plane's results (+ optional class max)
+            auto store_plane = [&](int k, const float (&acc)[R]) {
+                const int plane = b * C + k;
+                if (prm.dst_pair) {  // row pairs: 8-byte stores, 256 contiguous bytes per warp
+                    float2* __restrict__ op = reinterpret_cast<float2*>(prm.dst) +
+                                              ((size_t)plane * prm.Hp2 + (yw >> 1)) * prm.dst_pitch + x;
+                    const size_t pitch = (size_t)prm.dst_pitch;
+#pragma unroll
+                    for (int i = 0; i < R; i += 2, op += pitch)
+                        if (i < nrow) *op = make_float2(acc[i], acc[i + 1]);  // (odd H: row H lands in the allocation padding)
+                } else {  // last iteration: the caller's [B,C,H,W] tensor, coalesced 128-byte rows
+                    float* __restrict__ op = prm.dst + ((size_t)plane * H + yw) * prm.dst_pitch + x;
+                    const size_t pitch = (size_t)prm.dst_pitch;
+                    if (nrow == R) {
+#pragma unroll
+                        for (int i = 0; i < R; ++i, op += pitch) *op = acc[i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < R; ++i, op += pitch)
+                            if (i < nrow) *op = acc[i];
+                    }
+                }
+                if (prm.cls_max != nullptr) {  // last iteration only: keep its ALU work out of the other nine
+                    unsigned mx = 0u;
+#pragma unroll
+                    for (int i = 0; i < R; ++i)
+                        if (i < nrow) mx = max(mx, ordered_from_float(acc[i]));
+                    mx = __reduce_max_sync(0xffffffffu, mx);
+                    if (lane == 0 && mx != 0u) atomicMax(prm.cls_max + plane, mx);
+                }
+            };
+            auto group_sync = [&]() {
+                // immediate barrier ids: with a register id ptxas reserves all 16 named barriers
+                if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(NW * 32) : "memory");
+                else if (grp == 1) asm volatile("bar.sync 3, %0;" ::"n"(NW * 32) : "memory");
+                else if (grp == 2) asm volatile("bar.sync 4, %0;" ::"n"(NW * 32) : "memory");
+                else asm volatile("bar.sync 5, %0;" ::"n"(NW * 32) : "memory");
+            };
             int probe = 0;  // 1: the barriers of this group's next class were already seen complete
+            if constexpr (CPP == 2) {
+                // ---- two class planes per pass: pair p = classes 2p, 2p+1 -> group p % NG
+                const int npairs = (C + 1) / 2;
+                for (int pp = grp; pp < npairs; pp += NG) {
+                    const int k0 = 2 * pp, k1 = k0 + 1;
+                    const bool two = k1 < C;
+                    const long long sq0 = seq0 + k0, sq1 = sq0 + 1;
+                    const int bi0 = (int)(sq0 % NBAR), bi1 = (int)(sq1 % NBAR);
+                    PAMR_EV(grp, wq == 0 && lane == 0, 100 + k0);
+                    if (!probe) mbar_wait(smem_u32(&ctrl->tma_bar[bi0]), (uint32_t)(sq0 / NBAR) & 1u);
+                    if (two) mbar_wait(smem_u32(&ctrl->tma_bar[bi1]), (uint32_t)(sq1 / NBAR) & 1u);
+                    PAMR_EV(grp, wq == 0 && lane == 0, 6);
+                    float* slot0 = slots + (size_t)(sq0 % NSLOT) * C_::SLOT_FLOATS;
+                    float* slot1 = slots + (size_t)(sq1 % NSLOT) * C_::SLOT_FLOATS;
+                    if (border) {  // replicate padding: the group patches the halo rows of its own slots
+                        patch_window<R>(slot0, x0, y0, H, W, wq, lane);
+                        if (two) patch_window<R>(slot1, x0, y0, H, W, wq, lane);
+                        group_sync();
+                    }
+                    const int spo = ((wq * R + HALO) / 2) * ROWP + (lane + HALO) * 2;
+                    float acc0[R], acc1[R];
+#pragma unroll
+                    for (int i = 0; i < R; ++i) acc0[i] = acc1[i] = 0.f;
+#if defined(PAMR_EXPERIMENTS) && defined(PAMR_X_NOCHASE)    // timing experiment: no weight hand-over at all (wrong values)
+                    const bool first = false, last = false;
+#else
+                    const bool first = (pp == grp), last = (pp + NG >= npairs);
+#endif
+                    compute_pass2<R>(slot0 + spo, slot1 + spo, two, tbase, acc0, acc1, x, W, first ? filled0 : 0u, last ? free0 : 0u,
+                                     (uint32_t)ti & 1u, lane);
+                    if (cs_tile) {
+                        column_strip_pass<R>(prm, slot0, tbase, b * C + k0, y0, wq, lane);
+                        if (two) column_strip_pass<R>(prm, slot1, tbase, b * C + k1, y0, wq, lane);
+                        if (last) {  // this warp is done with the tile's strip weights
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(smem_u32(&ctrl->csw_free_bar));
+                        }
+                    }
+                    PAMR_EV(grp, wq == 0 && lane == 0, 9);
+                    __syncwarp();
+                    if (lane == 0) {  // release the slots as early as possible
+                        mbar_arrive(smem_u32(&ctrl->empty_bar[bi0]));
+                        if (two) mbar_arrive(smem_u32(&ctrl->empty_bar[bi1]));
+                    }
+                    probe = 0;
+                    if (pp + NG < npairs) {
+                        const long long sq2 = sq0 + 2 * NG;
+                        probe = (int)mbar_poll(smem_u32(&ctrl->tma_bar[sq2 % NBAR]), (uint32_t)(sq2 / NBAR) & 1u);
+                    }
+                    store_plane(k0, acc0);
+                    if (two) store_plane(k1, acc1);
+                    PAMR_EV(grp, wq == 0 && lane == 0, 8);
+                }
+            } else {
             for (int k = grp; k < C; k += NG) {
                 const long long sq = seq0 + k;
                 const int s = (int)(sq % NSLOT), bi = (int)(sq % NBAR);
@@ -770,12 +1121,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 float* slot = slots + (size_t)s * C_::SLOT_FLOATS;
                 if (border) {  // replicate padding: the group patches the halo rows of its own slot
                     patch_window<R>(slot, x0, y0, H, W, wq, lane);
-                    // immediate barrier ids: with a register id ptxas reserves all 16 named barriers and no
-                    // other CTA (the concurrent column strip) could share the SM
-                    if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(NW * 32) : "memory");
-                    else if (grp == 1) asm volatile("bar.sync 3, %0;" ::"n"(NW * 32) : "memory");
-                    else if (grp == 2) asm volatile("bar.sync 4, %0;" ::"n"(NW * 32) : "memory");
-                    else asm volatile("bar.sync 5, %0;" ::"n"(NW * 32) : "memory");
+                    group_sync();
                 }
                 const float* sp = slot + ((wq * R + HALO) / 2) * ROWP + (lane + HALO) * 2;
                 float acc[R];
@@ -806,36 +1152,9 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                     const long long sq2 = sq + NG;
                     probe = (int)mbar_poll(smem_u32(&ctrl->tma_bar[sq2 % NBAR]), (uint32_t)(sq2 / NBAR) & 1u);
                 }
-                // ---- store and optional class max
-                const int plane = b * C + k;
-                if (prm.dst_pair) {  // row pairs: 8-byte stores, 256 contiguous bytes per warp
-                    float2* __restrict__ op = reinterpret_cast<float2*>(prm.dst) +
-                                              ((size_t)plane * prm.Hp2 + (yw >> 1)) * prm.dst_pitch + x;
-                    const size_t pitch = (size_t)prm.dst_pitch;
-#pragma unroll
-                    for (int i = 0; i < R; i += 2, op += pitch)
-                        if (i < nrow) *op = make_float2(acc[i], acc[i + 1]);  // (odd H: row H lands in the allocation padding)
-                } else {  // last iteration: the caller's [B,C,H,W] tensor, coalesced 128-byte rows
-                    float* __restrict__ op = prm.dst + ((size_t)plane * H + yw) * prm.dst_pitch + x;
-                    const size_t pitch = (size_t)prm.dst_pitch;
-                    if (nrow == R) {
-#pragma unroll
-                        for (int i = 0; i < R; ++i, op += pitch) *op = acc[i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < R; ++i, op += pitch)
-                            if (i < nrow) *op = acc[i];
-                    }
-                }
-                if (prm.cls_max != nullptr) {  // last iteration only: keep its ALU work out of the other nine
-                    unsigned mx = 0u;
-#pragma unroll
-                    for (int i = 0; i < R; ++i)
-                        if (i < nrow) mx = max(mx, ordered_from_float(acc[i]));
-                    mx = __reduce_max_sync(0xffffffffu, mx);
-                    if (lane == 0 && mx != 0u) atomicMax(prm.cls_max + plane, mx);
-                }
+                store_plane(k, acc);
                 PAMR_EV(grp, wq == 0 && lane == 0, 8);
+            }
             }
         }
         // ---- row strip in the tail: the CTAs that own one tile fewer than the rest would idle during

@@ -18,7 +18,7 @@ namespace pamr {
 int pair_pitch(int W);
 int launch_repack_pairs(const float* src, float* dst, int planes, int H, int W, cudaStream_t s);
 int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, float* dst, int dst_pitch,
-                           bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s);
+                           bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int dev, bool dependent, cudaStream_t s);
 
 namespace {
 
@@ -276,7 +276,7 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, float* im
     for (int it = 0; it < iters; ++it) {
         const bool last = (it == iters - 1);
         float* dst = last ? m_out : P[next];
-        rc = launch_propagate_tuned(aff, tiling, src, dst, last ? W : Wp, !last, B, C, H, W, last ? cls_max : nullptr, dev, s);
+        rc = launch_propagate_tuned(aff, tiling, src, dst, last ? W : Wp, !last, B, C, H, W, last ? cls_max : nullptr, dev, it > 0, s);
         if (rc != PAMR_OK) return rc;
         src = dst;
         next ^= 1;

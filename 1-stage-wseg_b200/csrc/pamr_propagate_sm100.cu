@@ -176,6 +176,7 @@ __device__ __forceinline__ void tmem_wait_ld(float (&r)[16]) {
                  : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]),
                    "+f"(r[8]), "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]));
 }
+#if PAMR_CPP == 2
 // 32 / 8 / 4 consecutive columns (two-classes-per-pass kernel: one load per tap segment)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
     asm volatile(
@@ -211,6 +212,7 @@ __device__ __forceinline__ void tmem_wait_ld32(float* r) {
                    "+f"(r[16]), "+f"(r[17]), "+f"(r[18]), "+f"(r[19]), "+f"(r[20]), "+f"(r[21]), "+f"(r[22]), "+f"(r[23]),
                    "+f"(r[24]), "+f"(r[25]), "+f"(r[26]), "+f"(r[27]), "+f"(r[28]), "+f"(r[29]), "+f"(r[30]), "+f"(r[31]));
 }
+#endif  // PAMR_CPP == 2
 // plain bulk copy global -> shared memory, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -475,6 +477,7 @@ __device__ __forceinline__ void compute_pass(const float* __restrict__ sp, uint3
 #undef PAMR_ENTER_BATCH
 }
 
+#if PAMR_CPP == 2
 // ---- two classes per pass (CPP == 2) ----
 // The 48 taps are walked in 18 SEGMENTS of weights that share one register strip of class-plane rows: 6 for the
 // centre column (dilation id: taps dy = -d, +d; 2R TMEM columns) and 12 for the side columns ((bi, id): taps
@@ -688,6 +691,7 @@ __device__ __forceinline__ void compute_pass2(const float* __restrict__ sp0, con
 #undef PAMR_CENTRE
 #undef PAMR_SIDE
 }
+#endif  // PAMR_CPP == 2
 
 template <int R>
 __device__ __forceinline__ bool needs_patch(int y0, int H) {
@@ -859,6 +863,11 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // Programmatic dependent launch (iterations 2..T are launched with the attribute): the next iteration's CTAs may
+    // become resident as soon as SMs free up in this one's last wave, run their prologue and pull their first tile's
+    // weights -- which do not depend on this iteration -- and only their producer warp waits for this grid to finish
+    // (griddepcontrol.wait below) before it reads the class planes.  Both instructions are no-ops in a plain launch.
+    asm volatile("griddepcontrol.launch_dependents;");
 
     const int my_tiles = (prm.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int tiles_per_img = prm.tiles_x * prm.tiles_y;
@@ -878,6 +887,9 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         // n % NSLOT once sequence number n - NSLOT has been released.
         const long long total = (long long)my_tiles * C;
         [[maybe_unused]] int ev_n = 0;
+        // the class planes are the previous iteration's output (and this iteration's stores go to the buffer the previous
+        // one reads: every store depends on a plane that is loaded after this wait)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         for (long long n_issue = 0; n_issue < total; ++n_issue) {
             const int s = (int)(n_issue % NSLOT), bi = (int)(n_issue % NBAR);
             const int ti = (int)(n_issue / C), c = (int)(n_issue % C);
@@ -1056,7 +1068,8 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 else asm volatile("bar.sync 5, %0;" ::"n"(NW * 32) : "memory");
             };
             int probe = 0;  // 1: the barriers of this group's next class were already seen complete
-            if constexpr (CPP == 2) {
+#if PAMR_CPP == 2
+            {
                 // ---- two class planes per pass: pair p = classes 2p, 2p+1 -> group p % NG
                 const int npairs = (C + 1) / 2;
                 for (int pp = grp; pp < npairs; pp += NG) {
@@ -1110,7 +1123,9 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                     if (two) store_plane(k1, acc1);
                     PAMR_EV(grp, wq == 0 && lane == 0, 8);
                 }
-            } else {
+            }
+#else
+            {
             for (int k = grp; k < C; k += NG) {
                 const long long sq = seq0 + k;
                 const int s = (int)(sq % NSLOT), bi = (int)(sq % NBAR);
@@ -1156,6 +1171,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 PAMR_EV(grp, wq == 0 && lane == 0, 8);
             }
             }
+#endif
         }
         // ---- row strip in the tail: the CTAs that own one tile fewer than the rest would idle during
         //      the last wave; they compute the row strip y in [Ht,H) instead (no separate launch)
@@ -1237,7 +1253,7 @@ inline bool row_strip_in_tail(long long items, long long ntiles, int grid) {
 
 template <int R>
 int launch_one(const float* aff, const AffTiling& tiling, const float* src, int src_pitch, float* dst, int dst_pitch,
-               bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int sm_count, int dev, cudaStream_t s) {
+               bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int sm_count, int dev, bool dependent, cudaStream_t s) {
     using C_ = Cfg<R>;
     // function attributes are per device: set once per (kernel, device)
     static std::atomic<int> attr_set[64];
@@ -1283,7 +1299,25 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
         count_launch();
         PAMR_CUDA_TRY(cudaGetLastError());
     }
-    propagate_sm100_kernel<R><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, p);
+#ifdef PAMR_NO_PDL
+    dependent = false;
+#endif
+    if (dependent && !(Ht < H && p.tail_cta0 < 0)) {  // (no separate row-strip launch in between)
+        // launched behind the previous iteration's tile kernel with programmatic stream serialization
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(NTHREADS);
+        cfg.dynamicSmemBytes = C_::SMEM_BYTES;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PAMR_CUDA_TRY(cudaLaunchKernelEx(&cfg, propagate_sm100_kernel<R>, tmap, p));
+    } else {
+        propagate_sm100_kernel<R><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, p);
+    }
     count_launch();
     PAMR_CUDA_TRY(cudaGetLastError());
     return PAMR_OK;
@@ -1403,7 +1437,7 @@ int launch_repack_pairs(const float* src, float* dst, int planes, int H, int W, 
 // last wave has room, the row strip) and otherwise a small row-strip launch.  src is in the row-pair layout
 // (pitch pair_pitch(W), 16-byte aligned base); dst is in the row-pair layout (dst_pair) or the caller's standard layout.
 int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, float* dst, int dst_pitch,
-                           bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int dev, cudaStream_t s) {
+                           bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int dev, bool dependent, cudaStream_t s) {
     int sm_count = 0;
     int rc = device_sm_count(dev, &sm_count);
     if (rc != PAMR_OK) return rc;
@@ -1411,9 +1445,9 @@ int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, cons
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: source / affinity base not 16-byte aligned");
     const int sp = pair_pitch(W);
     if (tiling.R == 8)
-        return launch_one<8>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, cls_max, sm_count, dev, s);
+        return launch_one<8>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, cls_max, sm_count, dev, dependent, s);
     if (tiling.R == 10)
-        return launch_one<10>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, cls_max, sm_count, dev, s);
+        return launch_one<10>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, cls_max, sm_count, dev, dependent, s);
     return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: unsupported tiling R=%d", tiling.R);
 }
 

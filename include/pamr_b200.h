@@ -33,6 +33,13 @@ extern "C" {
 
 #define PAMR_B200_ABI_VERSION 2
 
+/* The library is built with hidden visibility; only the functions declared here are exported. */
+#if defined(__GNUC__)
+#define PAMR_API __attribute__((visibility("default")))
+#else
+#define PAMR_API
+#endif
+
 #define PAMR_OK 0
 #define PAMR_ERR_INVALID_ARGUMENT 1
 #define PAMR_ERR_CUDA 2
@@ -44,25 +51,25 @@ extern "C" {
 typedef void* pamr_stream_t; /* cudaStream_t */
 
 /* ABI version of the loaded library (== PAMR_B200_ABI_VERSION it was built with). */
-int pamr_b200_abi_version(void);
+PAMR_API int pamr_b200_abi_version(void);
 
 /* Thread-local description of the last error returned to this thread ("" if none). */
-const char* pamr_last_error(void);
+PAMR_API const char* pamr_last_error(void);
 
 /* Device facts used by the host side (SM count for persistent grids, L2 size for bench flushes).
  * Any output pointer may be NULL. */
-int pamr_device_info(int dev, int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
+PAMR_API int pamr_device_info(int dev, int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
 
 /* Number of kernels this library has launched since load (all threads); bench.py reports the
  * delta over its timed region as `gpu_launches`. */
-unsigned long long pamr_launch_count(void);
+PAMR_API unsigned long long pamr_launch_count(void);
 
 /*
  * F.interpolate(x, size, mode="bilinear", align_corners=True) on n_planes = B*Ch planes.
  * Replaces: pamr.py:125 (mask -> image size), models/SoftMaxAE.py:177 (image -> mask size).
  * src [n_planes,h,w] -> dst [n_planes,H,W]; same arithmetic as torch's CPU kernel.
  */
-int pamr_resize_bilinear_f32(const float* src, float* dst, int n_planes, int h, int w, int H, int W,
+PAMR_API int pamr_resize_bilinear_f32(const float* src, float* dst, int n_planes, int h, int w, int H, int W,
                              int dev, pamr_stream_t stream);
 
 /*
@@ -70,7 +77,7 @@ int pamr_resize_bilinear_f32(const float* src, float* dst, int n_planes, int h, 
  * mean over channels, softmax over the 8*nd neighbours).
  * img [B,K,H,W] -> aff [B,8*nd,H,W]; each pixel's 8*nd weights sum to 1.
  */
-int pamr_affinity_f32(const float* img, float* aff, int B, int K, int H, int W, const int* dilations,
+PAMR_API int pamr_affinity_f32(const float* img, float* aff, int B, int K, int H, int W, const int* dilations,
                       int nd, int dev, pamr_stream_t stream);
 
 /*
@@ -78,7 +85,7 @@ int pamr_affinity_f32(const float* img, float* aff, int B, int K, int H, int W, 
  * (3x3 neighbourhood incl. the centre at every dilation, replicate padding) of every pixel and channel.
  * img [B,K,H,W] -> sd [B,K,H,W]  (the reference returns the same values as [B,K,1,H,W]).  B*K <= 65535.
  */
-int pamr_local_std_f32(const float* img, float* sd, int B, int K, int H, int W, const int* dilations,
+PAMR_API int pamr_local_std_f32(const float* img, float* sd, int B, int K, int H, int W, const int* dilations,
                        int nd, int dev, pamr_stream_t stream);
 
 /*
@@ -92,8 +99,8 @@ int pamr_local_std_f32(const float* img, float* sd, int B, int K, int H, int W, 
  * ordered encoding of pamr_ordered_from_float() (fused into the last step; saves the max pass of
  * pseudo_gtmask, SoftMaxAE.py:35, when no resize follows).  The call initialises it.
  */
-size_t pamr_propagate_scratch_bytes(int B, int C, int H, int W, const int* dilations, int nd, int iters);
-int pamr_propagate_f32(const float* aff, const float* m_in, float* m_out, void* scratch, size_t scratch_bytes,
+PAMR_API size_t pamr_propagate_scratch_bytes(int B, int C, int H, int W, const int* dilations, int nd, int iters);
+PAMR_API int pamr_propagate_f32(const float* aff, const float* m_in, float* m_out, void* scratch, size_t scratch_bytes,
                        int B, int C, int H, int W, const int* dilations, int nd, int iters,
                        unsigned* cls_max, int dev, pamr_stream_t stream);
 
@@ -103,9 +110,9 @@ int pamr_propagate_f32(const float* aff, const float* m_in, float* m_out, void* 
  * `iters` propagation steps into out [B,C,H,W].  workspace: device scratch of at least
  * pamr_forward_workspace_bytes(...) bytes, 256-byte aligned.
  */
-size_t pamr_forward_workspace_bytes(int B, int K, int C, int H, int W, int h, int w, const int* dilations,
+PAMR_API size_t pamr_forward_workspace_bytes(int B, int K, int C, int H, int W, int h, int w, const int* dilations,
                                     int nd, int iters);
-int pamr_forward_f32(const float* img, const float* mask, float* out, void* workspace,
+PAMR_API int pamr_forward_f32(const float* img, const float* mask, float* out, void* workspace,
                      size_t workspace_bytes, int B, int K, int C, int H, int W, int h, int w,
                      const int* dilations, int nd, int iters, unsigned* cls_max, int dev,
                      pamr_stream_t stream);
@@ -117,7 +124,7 @@ int pamr_forward_f32(const float* img, const float* mask, float* out, void* work
  * cleaned: NULL or [B,C,H,W] receiving v;  cls_max: NULL or [B,C] receiving max over pixels of v
  * (ordered encoding; initialised by the call).
  */
-int pamr_clean_f32(const float* m, const float* labels, float* cleaned, unsigned* cls_max, int B, int C,
+PAMR_API int pamr_clean_f32(const float* m, const float* labels, float* cleaned, unsigned* cls_max, int B, int C,
                    int h, int w, int H, int W, int dev, pamr_stream_t stream);
 
 /*
@@ -133,7 +140,7 @@ int pamr_clean_f32(const float* m, const float* labels, float* cleaned, unsigned
  * class_count: NULL or int32 [B,C] receiving the number of pixels assigned to each class
  * (num_pixels_per_class of balanced_mask_loss_ce, SoftMaxAE.py:72; initialised by the call).
  */
-int pamr_pseudo_labels_f32(const float* m, const float* labels, const unsigned* cls_max, uint8_t* label,
+PAMR_API int pamr_pseudo_labels_f32(const float* m, const float* labels, const unsigned* cls_max, uint8_t* label,
                            float* pseudo_gt, int* class_count, int B, int C, int h, int w, int H, int W,
                            float bg_cut, float fg_cut, float low_cut, int cls_max_gated, int dev,
                            pamr_stream_t stream);
@@ -157,13 +164,13 @@ int pamr_pseudo_labels_f32(const float* m, const float* labels, const unsigned* 
  * pamr_mask_ce_backward_f32: grad_logits [B,C,h,w] = d(sum_b grad_loss[b]*loss[b]) / d logits, from the
  * same logits / label map and the workspace the forward call filled.  Deterministic (gather, no atomics).
  */
-size_t pamr_mask_ce_workspace_bytes(int B, int C, int h, int w, int H, int W);
-int pamr_labels_from_onehot_f32(const float* pseudo_gt, uint8_t* label, int* class_count, int B, int C, int H, int W,
+PAMR_API size_t pamr_mask_ce_workspace_bytes(int B, int C, int h, int w, int H, int W);
+PAMR_API int pamr_labels_from_onehot_f32(const float* pseudo_gt, uint8_t* label, int* class_count, int B, int C, int H, int W,
                                 int dev, pamr_stream_t stream);
-int pamr_mask_ce_forward_f32(const float* logits, const uint8_t* label, const int* class_count, const float* gt_labels,
+PAMR_API int pamr_mask_ce_forward_f32(const float* logits, const uint8_t* label, const int* class_count, const float* gt_labels,
                              float* loss, void* workspace, size_t workspace_bytes, int B, int C, int h, int w, int H,
                              int W, int dev, pamr_stream_t stream);
-int pamr_mask_ce_backward_f32(const float* logits, const uint8_t* label, const float* grad_loss, float* grad_logits,
+PAMR_API int pamr_mask_ce_backward_f32(const float* logits, const uint8_t* label, const float* grad_loss, float* grad_logits,
                               const void* workspace, size_t workspace_bytes, int B, int C, int h, int w, int H, int W,
                               int dev, pamr_stream_t stream);
 
@@ -174,7 +181,7 @@ int pamr_mask_ce_backward_f32(const float* logits, const uint8_t* label, const f
  * (multiply and add rounded separately, as mul_().add_() does; with h == H and w == W it is the plain denorm).
  * mean_host / std_host: HOST arrays of K floats, K <= 8.  img_norm [B,K,h,w] -> dst [B,K,H,W].
  */
-int pamr_denorm_resize_f32(const float* img_norm, const float* mean_host, const float* std_host, float* dst, int B,
+PAMR_API int pamr_denorm_resize_f32(const float* img_norm, const float* mean_host, const float* std_host, float* dst, int B,
                            int K, int h, int w, int H, int W, int dev, pamr_stream_t stream);
 
 /*
@@ -187,7 +194,7 @@ int pamr_denorm_resize_f32(const float* img_norm, const float* mean_host, const 
  * merged: NULL or float [C,H,W];  pred: NULL or uint8 [H,W].  S <= 16.
  * (The reference moves the [S,C,Hp,Wp] scores to the host for this; here only the uint8 map has to.)
  */
-int pamr_merge_multiscale_f32(const float* masks, const int* pads_host, const float* labels, float* merged,
+PAMR_API int pamr_merge_multiscale_f32(const float* masks, const int* pads_host, const float* labels, float* merged,
                               uint8_t* pred, int S, int C, int Hp, int Wp, int H, int W, int flip, float bg_pow,
                               float prospect_thresh, int dev, pamr_stream_t stream);
 
@@ -198,15 +205,15 @@ int pamr_merge_multiscale_f32(const float* masks, const int* pads_host, const fl
  * synchronises the stream it created.  h_img [B,K,H,W], h_mask [B,C,h,w], h_labels [B,C-1] or NULL,
  * h_label [B,H,W] uint8.  Device scratch is allocated and freed inside the call.
  */
-int pamr_pseudo_labels_host_f32(const float* h_img, const float* h_mask, const float* h_labels,
+PAMR_API int pamr_pseudo_labels_host_f32(const float* h_img, const float* h_mask, const float* h_labels,
                                 uint8_t* h_label, int B, int K, int C, int H, int W, int h, int w,
                                 const int* dilations, int nd, int iters, float bg_cut, float fg_cut,
                                 float low_cut, int dev);
 
 /* Ordered unsigned encoding of a float (monotone: a < b  <=>  enc(a) < enc(b)); 0 is below every
  * float.  Host helpers for reading cls_max. */
-unsigned pamr_ordered_from_float(float v);
-float pamr_float_from_ordered(unsigned u);
+PAMR_API unsigned pamr_ordered_from_float(float v);
+PAMR_API float pamr_float_from_ordered(unsigned u);
 
 #ifdef __cplusplus
 }

@@ -405,6 +405,9 @@ def test_local_std_vs_oracle():
         rel = float((np.abs(got - ref) / np.maximum(ref, 1e-3)).max())
         print("local std, %s: max-abs %.3g, max-rel %.3g (floor 1e-3)" % (fam, err, rel))
         assert got.shape == ref.shape and err <= 2e-7 and rel <= 2e-6
+    # the module form returns the reference's shape [B,K,1,H,W] (pamr.py:103, keepdim over the sample axis)
+    mod = wseg_b200.PAMR(10, D6).to(DEV).aff_std(G(image))
+    assert tuple(mod.shape) == (2, 3, 1, 90, 130) and np.array_equal(N(mod)[:, :, 0], got)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")

@@ -413,10 +413,22 @@ affinity_tile_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const AtPar
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(ctrl->tmem_base), "r"(512));
 }
 
-// [planes][H][W] -> [planes][H][pitch] (pitch = W rounded up to 4 floats; the padding is never read)
+// [planes][H][W] -> [planes][H][pitch] (pitch = W rounded up to 4 floats; the padding is never read).  One thread per
+// 16 bytes of the destination: four scalar loads (the source rows have no alignment), one 128-bit store.
 __global__ void __launch_bounds__(256) pitch_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int W, int pitch, size_t rows) {
-    for (size_t r = blockIdx.x; r < rows; r += gridDim.x)
-        for (int x = threadIdx.x; x < W; x += blockDim.x) dst[r * pitch + x] = __ldg(src + r * W + x);
+    const int q4 = pitch >> 2;  // float4 per destination row
+    const size_t n = rows * (size_t)q4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / q4;
+        const int x = (int)(i - r * q4) * 4;
+        const float* __restrict__ p = src + r * W + x;
+        float4 v;
+        v.x = __ldg(p);
+        v.y = (x + 1 < W) ? __ldg(p + 1) : 0.f;
+        v.z = (x + 2 < W) ? __ldg(p + 2) : 0.f;
+        v.w = (x + 3 < W) ? __ldg(p + 3) : 0.f;
+        reinterpret_cast<float4*>(dst)[i] = v;
+    }
 }
 
 template <int R, int K>
@@ -510,7 +522,7 @@ int launch_affinity(const float* img, float* aff, int B, int K, int H, int W, co
             if (pitching) {
                 pitch = (W + 3) & ~3;
                 const size_t rows = (size_t)B * K * H;
-                pitch_rows_kernel<<<(unsigned)(rows < 148 * 32 ? rows : 148 * 32), 256, 0, s>>>(img, img_pitched, W, pitch, rows);
+                pitch_rows_kernel<<<(unsigned)((rows * (pitch >> 2) + 255) / 256 < 148 * 16 ? (rows * (pitch >> 2) + 255) / 256 : 148 * 16), 256, 0, s>>>(img, img_pitched, W, pitch, rows);
                 count_launch();
                 PAMR_CUDA_TRY(cudaGetLastError());
                 src = img_pitched;

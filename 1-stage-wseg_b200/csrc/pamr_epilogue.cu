@@ -66,8 +66,9 @@ constexpr int PL_THREADS = 256;
 
 // One thread per output pixel, loops over the C classes (coalesced plane reads).
 // grid: (ceil(H*W/256), B)
-constexpr int PL_BATCH = 7;  // 21 classes = 3 batches
-template <bool kResize>
+// PL_BATCH class planes are loaded before the first compare: 7 (21 classes = 3 batches) when the values are
+// interpolated (4 loads each), 21 when they are read directly -- a thread then has all of its 84 bytes in flight
+template <bool kResize, int PL_BATCH>
 __global__ void __launch_bounds__(PL_THREADS)
 pseudo_labels_kernel(const float* __restrict__ m, const float* __restrict__ labels,
                      const unsigned* __restrict__ cls_max, uint8_t* __restrict__ label,
@@ -260,12 +261,16 @@ int launch_pseudo_labels(const float* m, const float* labels, const unsigned* cl
     dim3 grid((unsigned)((HW + PL_THREADS - 1) / PL_THREADS), B);
     const size_t smem = sizeof(float) * 3 * (size_t)C;
     if (smem > 48 * 1024) return set_error(PAMR_ERR_INVALID_ARGUMENT, "pseudo_labels: C too large");
-    if (h == H && w == W)
-        pseudo_labels_kernel<false><<<grid, PL_THREADS, smem, s>>>(m, labels, cls_max, label, pseudo_gt, class_count,
-                                                                   C, h, w, H, W, 0.f, 0.f, bg_cut, fg_cut, low_cut,
-                                                                   max_is_gated);
+    if (h == H && w == W && C > 14)
+        pseudo_labels_kernel<false, 21><<<grid, PL_THREADS, smem, s>>>(m, labels, cls_max, label, pseudo_gt, class_count,
+                                                                       C, h, w, H, W, 0.f, 0.f, bg_cut, fg_cut, low_cut,
+                                                                       max_is_gated);
+    else if (h == H && w == W)
+        pseudo_labels_kernel<false, 7><<<grid, PL_THREADS, smem, s>>>(m, labels, cls_max, label, pseudo_gt, class_count,
+                                                                      C, h, w, H, W, 0.f, 0.f, bg_cut, fg_cut, low_cut,
+                                                                      max_is_gated);
     else
-        pseudo_labels_kernel<true><<<grid, PL_THREADS, smem, s>>>(m, labels, cls_max, label, pseudo_gt, class_count,
+        pseudo_labels_kernel<true, 7><<<grid, PL_THREADS, smem, s>>>(m, labels, cls_max, label, pseudo_gt, class_count,
                                                                   C, h, w, H, W, scale_of(h, H), scale_of(w, W),
                                                                   bg_cut, fg_cut, low_cut, max_is_gated);
     count_launch();

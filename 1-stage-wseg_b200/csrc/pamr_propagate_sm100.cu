@@ -364,9 +364,19 @@ __device__ __forceinline__ void signal_free(uint32_t bar, int lane) {
 // below the image ever need patching in shared memory.
 // filled_bar != 0: first pass of the tile, wait per unit for the fill warp (phase parity par);
 // free_bar != 0: last pass of the tile, release every unit after its last read.
+#ifdef PAMR_PASS_SPECIALISED
+template <int R, bool FIRST, bool LAST>
+#else
 template <int R>
+#endif
 __device__ __forceinline__ void compute_pass(const float* __restrict__ sp, uint32_t tbase, float (&acc)[R], int xg, int W,
-                                             uint32_t filled_bar, uint32_t free_bar, uint32_t par, int lane) {
+                                             uint32_t filled_bar_, uint32_t free_bar_, uint32_t par, int lane) {
+#ifdef PAMR_PASS_SPECIALISED
+    // first / last pass of a tile as separate instantiations: the five middle passes carry no hand-over branches
+    const uint32_t filled_bar = FIRST ? filled_bar_ : 0u, free_bar = LAST ? free_bar_ : 0u;
+#else
+    const uint32_t filled_bar = filled_bar_, free_bar = free_bar_;
+#endif
     using L = TmemLayout<R>;
     // The weights stream through two 16-register buffers in consumption order: batch b (TMEM columns
     // [16b, 16b+16)) lives in wb[b & 1] and belongs to chunk b / BPC.  All indices are compile-time.
@@ -1147,7 +1157,14 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
 #else
                 const bool first = (k == grp), last = (k + NG >= C);
 #endif
+#ifdef PAMR_PASS_SPECIALISED
+                if (first && last) compute_pass<R, true, true>(sp, tbase, acc, x, W, filled0, free0, (uint32_t)ti & 1u, lane);
+                else if (first) compute_pass<R, true, false>(sp, tbase, acc, x, W, filled0, free0, (uint32_t)ti & 1u, lane);
+                else if (last) compute_pass<R, false, true>(sp, tbase, acc, x, W, filled0, free0, (uint32_t)ti & 1u, lane);
+                else compute_pass<R, false, false>(sp, tbase, acc, x, W, filled0, free0, (uint32_t)ti & 1u, lane);
+#else
                 compute_pass<R>(sp, tbase, acc, x, W, first ? filled0 : 0u, last ? free0 : 0u, (uint32_t)ti & 1u, lane);
+#endif
                 if (cs_tile) {
                     column_strip_pass<R>(prm, slot, tbase, b * C + k, y0, wq, lane);
                     if (last) {  // this warp is done with the tile's strip weights

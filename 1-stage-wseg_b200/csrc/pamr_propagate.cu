@@ -16,6 +16,7 @@ namespace pamr {
 
 // pamr_propagate_sm100.cu
 int pair_pitch(int W);
+int pair_rows_padded(int H);
 int launch_repack_pairs(const float* src, float* dst, int planes, int H, int W, cudaStream_t s);
 int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, float* dst, int dst_pitch,
                            bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int dev, bool dependent, cudaStream_t s);
@@ -112,7 +113,7 @@ ScratchPlan plan_scratch(int B, int C, int H, int W, const Dilations& dil, int i
     if (t.R > 0) {
         // tuned kernel: two ping-pong buffers in the row-pair layout [B*C][ceil(H/2)][Wp][2], Wp a multiple of 16
         // (TMA reads 64-bit elements and needs 16-byte global strides; whole 128-byte lines per row pair)
-        p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * ((H + 1) / 2) * pair_pitch(W) * 2, 256);
+        p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * pair_rows_padded(H) * pair_pitch(W) * 2, 256);
         if (!aff_is_tiled) p.aff_tiled = align_up(sizeof(float) * t.floats, 256);
     } else {
         p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * H * W, 256);

@@ -26,7 +26,8 @@
 //  * a producer warp streams the class planes of the tile (+24 px halo, 80 x (4R+48) floats) through a
 //    4-slot shared-memory ring with TMA (cp.async.bulk.tensor.3d over 64-bit elements = row pairs) +
 //    mbarriers; TMA zero-fills outside the image; replicate padding (pamr.py:50) in x is a per-lane
-//    clamped column offset, in y the consuming group patches the halo rows of top / bottom tiles;
+//    clamped column offset, in y it is DATA: the planes carry 24 replicated rows above and below the image, written by
+//    whoever writes row 0 / row H-1 (no patching of the window in shared memory);
 //  * FP32 math as packed FFMA2 over adjacent rows; the per-(b,c) max for pseudo_gtmask is fused into
 //    the last iteration (warp reduce + atomicMax);
 //  * remainders (W = H = 321 -> one column, one row): a column strip of at most 2 columns is computed by the
@@ -304,14 +305,31 @@ std::atomic<int> g_timeline_cta{0}, g_timeline_skip{0};
 #define PAMR_EV(stream, cond, code) do { } while (0)
 #endif
 
-// element (y, x) of a plane in the row-pair layout
+// element (y, x) of a window / an unpadded plane in the row-pair layout
 __host__ __device__ __forceinline__ size_t pair_index(int pitch, int y, int x) {
     return ((size_t)(y >> 1) * pitch + x) * 2 + (y & 1);
 }
+// Planes of the ping-pong buffers carry PADP replicated row pairs above row 0 and below row H-1 (replicate padding in
+// y, pamr.py:50, as DATA: whoever writes row 0 / row H-1 also writes the 24 rows beyond it), so that the TMA window of
+// a tile on the top / bottom image border needs no patching.  Hp2 in Params counts the padded row pairs.
+constexpr int PADP = HALO / 2;
+__host__ __device__ __forceinline__ int padded_pairs(int H) { return (H + 1) / 2 + 2 * PADP; }
+__host__ __device__ __forceinline__ size_t plane_index(int pitch, int y, int x) {  // y in [-HALO, H + HALO)
+    return ((size_t)((y + HALO) >> 1) * pitch + x) * 2 + ((y + HALO) & 1);
+}
 __device__ __forceinline__ size_t src_plane_stride(const Params& p) { return (size_t)p.Hp2 * p.src_pitch * 2; }
 __device__ __forceinline__ float* dst_pixel(const Params& p, int plane, int y, int x) {
-    return p.dst_pair ? p.dst + (size_t)plane * p.Hp2 * p.dst_pitch * 2 + pair_index(p.dst_pitch, y, x)
+    return p.dst_pair ? p.dst + (size_t)plane * p.Hp2 * p.dst_pitch * 2 + plane_index(p.dst_pitch, y, x)
                       : p.dst + ((size_t)plane * p.H + y) * p.dst_pitch + x;
+}
+// rows beyond the image that repeat row y (y == 0: the 24 rows above; y == H-1: the rows below, including the second
+// half of the last row pair when H is odd); none for any other row
+__device__ __forceinline__ void store_replicas(const Params& p, int plane, int y, int x, float v) {
+    if (!p.dst_pair) return;
+    if (y == 0)
+        for (int r = -HALO; r < 0; ++r) *dst_pixel(p, plane, r, x) = v;
+    if (y == p.H - 1)
+        for (int r = p.H; r < 2 * (((p.H + 1) >> 1)) + HALO; ++r) *dst_pixel(p, plane, r, x) = v;
 }
 
 // ---------------------------------------------------------------- TMEM weight layout
@@ -361,7 +379,7 @@ __device__ __forceinline__ void signal_free(uint32_t bar, int lane) {
 // slot + ((R*wq + HALO)/2)*ROWP + (lane + HALO)*2; neighbours are immediate offsets.
 // xg = this lane's image column, W = image width: the side columns are addressed with a per-lane offset
 // clamp(xg +- d, 0, W-1) - xg, which implements replicate padding in x for free, so only rows above /
-// below the image ever need patching in shared memory.
+// below the image are ever an issue (they are replicated rows of the padded planes).
 // filled_bar != 0: first pass of the tile, wait per unit for the fill warp (phase parity par);
 // free_bar != 0: last pass of the tile, release every unit after its last read.
 #ifdef PAMR_PASS_SPECIALISED
@@ -703,40 +721,6 @@ __device__ __forceinline__ void compute_pass2(const float* __restrict__ sp0, con
 }
 #endif  // PAMR_CPP == 2
 
-template <int R>
-__device__ __forceinline__ bool needs_patch(int y0, int H) {
-    // replicate padding in x is handled by the per-lane column offsets
-    return y0 < HALO || y0 + Cfg<R>::TY + HALO > H;
-}
-
-// Border tiles: TMA zero-filled everything outside the tensor, and for odd H the second row of the last
-// row pair is allocation padding; overwrite every window row outside the image with the clamped
-// (replicate-padded, pamr.py:50) row.  Window element (wy,wx) <-> image pixel (y0-24+wy, x0-24+wx).
-// Executed by the NW warps of the compute group that is about to read the slot (wq = warp in group).
-// Every store targets an out-of-image element and every load an in-image one, so the four warps
-// need no ordering among themselves; the caller synchronises the group afterwards.
-template <int R>
-__device__ __forceinline__ void patch_window(float* slot, int x0, int y0, int H, int W, int wq, int lane) {
-    constexpr int WIN_H = Cfg<R>::WIN_H;
-    const int vx0 = max(0, HALO - x0), vx1 = min(WIN_W, W - x0 + HALO);  // in-image columns [vx0, vx1)
-    const int vy0 = max(0, HALO - y0), vy1 = min(WIN_H, H - y0 + HALO);  // in-image rows    [vy0, vy1)
-#pragma unroll
-    for (int k = 0; k < (WIN_W + 31) / 32; ++k) {
-        const int wx = 32 * k + lane;
-        if (wx < WIN_W) {
-            const int sx = min(max(wx, vx0), vx1 - 1);
-            if (vy0 > 0) {
-                const float v = slot[pair_index(WIN_P, vy0, sx)];
-                for (int wy = wq; wy < vy0; wy += NW) slot[pair_index(WIN_P, wy, wx)] = v;
-            }
-            if (vy1 < WIN_H) {
-                const float v = slot[pair_index(WIN_P, vy1 - 1, sx)];
-                for (int wy = vy1 + wq; wy < WIN_H; wy += NW) slot[pair_index(WIN_P, wy, wx)] = v;
-            }
-        }
-    }
-}
-
 // Row strip.  The tiles cover [0,Wt) x [0,Ht); a remainder of at most RS_MAX_H rows (H = 321 -> one row) is not
 // worth a tile row of its own.  It is cut into work items of 32 consecutive pixels of one row of one plane (one
 // pixel per lane, neighbours straight from global memory / L2 with clamped coordinates, weights from the
@@ -759,9 +743,12 @@ __device__ __forceinline__ void strip_item(const Params& prm, int item, int lane
         const int p = seq_tap(s), d = dil_of(p >> 3), j = p & 7;
         const int yy = clampi(y + tap_dy(j) * d, 0, H - 1);
         const int xx = clampi(xc + tap_dx(j) * d, 0, W - 1);
-        acc = fmaf(__ldg(wp + (size_t)s * W), __ldg(pl + pair_index(prm.src_pitch, yy, xx)), acc);
+        acc = fmaf(__ldg(wp + (size_t)s * W), __ldg(pl + plane_index(prm.src_pitch, yy, xx)), acc);
     }
-    if (valid) *dst_pixel(prm, plane, y, x) = acc;
+    if (valid) {
+        *dst_pixel(prm, plane, y, x) = acc;
+        store_replicas(prm, plane, y, x, acc);
+    }
     if (prm.cls_max != nullptr) {
         const unsigned m = __reduce_max_sync(0xffffffffu, valid ? ordered_from_float(acc) : 0u);
         if (lane == 0 && m != 0u) atomicMax(prm.cls_max + plane, m);
@@ -792,7 +779,7 @@ constexpr CsOffsets make_cs_offsets() {
 __constant__ CsOffsets c_cs = make_cs_offsets();
 
 // Column strip x = Wt = W-1, computed by the tiles on the right image border (x0 + 32 == Wt) after every class
-// pass from the window the warp just used (rows outside the image have been patched).  LP = 32/R lanes share a
+// pass from the window the warp just used (rows outside the image are the planes' replicated rows).  LP = 32/R lanes share a
 // strip pixel: lane i*LP + part of warp wq takes taps [part*TPL, (part+1)*TPL) of pixel (row wq*R + i of the tile);
 // the parts run one after the other on the same accumulator (handed on by shuffle), i.e. ONE FMA chain in
 // tap-sequence order, bit-identical to every other path.  The lane's TPL weights come from its spare TMEM columns
@@ -829,7 +816,10 @@ __device__ PAMR_CS_INLINE void column_strip_pass(const Params& prm, const float*
     }
     const int y = y0 + row;
     const bool valid = active && part == LP - 1 && y < prm.H;
-    if (valid) *dst_pixel(prm, plane, y, prm.Wt) = acc;
+    if (valid) {
+        *dst_pixel(prm, plane, y, prm.Wt) = acc;
+        store_replicas(prm, plane, y, prm.Wt, acc);
+    }
     if (prm.cls_max != nullptr) {
         const unsigned m = __reduce_max_sync(0xffffffffu, valid ? ordered_from_float(acc) : 0u);
         if (lane == 0 && m != 0u) atomicMax(prm.cls_max + plane, m);
@@ -892,8 +882,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
     if (warp == W_PRODUCER) {
         // ===================== producer warp: TMA issue of the class planes =====================
         // Sequence number n = (tile_iter, class) -> slot n % NSLOT, barrier pair n % NBAR.  A consumer
-        // group waits for tma_bar (bytes landed), patches the halo itself if the tile touches the image
-        // border, computes, and releases the slot through empty_bar; the producer may refill slot
+        // group waits for tma_bar (bytes landed), computes, and releases the slot through empty_bar; the producer may refill slot
         // n % NSLOT once sequence number n - NSLOT has been released.
         const long long total = (long long)my_tiles * C;
         [[maybe_unused]] int ev_n = 0;
@@ -915,14 +904,14 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive_expect_tx(bar, C_::SLOT_BYTES);
                 // 64-bit elements = row pairs: coordinates (column, row pair, plane)
-                tma_load_3d(smem_u32(slots + (size_t)s * C_::SLOT_FLOATS), &tmap, bar, x0 - HALO, (y0 - HALO) / 2, b * C + c);
+                tma_load_3d(smem_u32(slots + (size_t)s * C_::SLOT_FLOATS), &tmap, bar, x0 - HALO, y0 / 2, b * C + c);  // (y0 - HALO) / 2 + PADP
                 if (PF_PLANES > 0 && n_issue + PF_PLANES < total) {  // pull a later plane window from HBM into L2
                     const long long np = n_issue + PF_PLANES;
                     const int pti = (int)(np / C), pc = (int)(np % C);
                     const int ptile = (int)blockIdx.x + pti * (int)gridDim.x;
                     const int pb = ptile / tiles_per_img, pt = ptile % tiles_per_img;
                     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-                                 ::"l"(&tmap), "r"((pt % prm.tiles_x) * TX - HALO), "r"(((pt / prm.tiles_x) * C_::TY - HALO) / 2), "r"(pb * C + pc)
+                                 ::"l"(&tmap), "r"((pt % prm.tiles_x) * TX - HALO), "r"(((pt / prm.tiles_x) * C_::TY) / 2), "r"(pb * C + pc)
                                  : "memory");
                 }
             }
@@ -1030,7 +1019,6 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             const int x = x0 + lane, yw = y0 + wq * R;
             const bool xok = x < W;
             const long long seq0 = (long long)ti * C;
-            const bool border = needs_patch<R>(y0, H);
             const int nrow = xok ? max(0, min(R, H - yw)) : 0;  // rows of this thread inside the image
             const bool cs_tile = wc > 0 && (t % prm.tiles_x == prm.tiles_x - 1);  // this tile also computes the column strip
             if (cs_tile && grp < active_groups) {
@@ -1042,13 +1030,35 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             // ---- store of one class plane's results (+ optional class max)
             auto store_plane = [&](int k, const float (&acc)[R]) {
                 const int plane = b * C + k;
+                [[maybe_unused]] float acc_fix = 0.f;
                 if (prm.dst_pair) {  // row pairs: 8-byte stores, 256 contiguous bytes per warp
                     float2* __restrict__ op = reinterpret_cast<float2*>(prm.dst) +
-                                              ((size_t)plane * prm.Hp2 + (yw >> 1)) * prm.dst_pitch + x;
+                                              ((size_t)plane * prm.Hp2 + PADP + (yw >> 1)) * prm.dst_pitch + x;
                     const size_t pitch = (size_t)prm.dst_pitch;
+                    // replicate padding as data: the owner of row 0 / row H-1 also fills the 24 rows beyond it (a warp-uniform
+                    // case: only the first warp of the top tiles and the warp that holds row H-1)
+                    const int il = H - 1 - yw;  // index of row H-1 in this thread's strip, if it is there
+                    if (yw == 0 && xok) {
+                        const float2 v = make_float2(acc[0], acc[0]);
+                        float2* __restrict__ pp = op - (size_t)PADP * pitch;
+#pragma unroll
+                        for (int r = 0; r < PADP; ++r, pp += pitch) *pp = v;
+                    }
+                    if (il >= 0 && il < R && xok) {
+                        float vl = acc[0];
+#pragma unroll
+                        for (int i = 1; i < R; ++i)
+                            if (i == il) vl = acc[i];
+                        float2* __restrict__ pp = op + (size_t)((il >> 1) + 1) * pitch;  // the pair after the one that holds row H-1
+#pragma unroll
+                        for (int r = 0; r < PADP; ++r, pp += pitch) *pp = make_float2(vl, vl);
+#pragma unroll
+                        for (int i = 0; i < R; i += 2)  // odd H: the second half of the last pair repeats row H-1 as well
+                            if (i == il) acc_fix = vl;
+                    }
 #pragma unroll
                     for (int i = 0; i < R; i += 2, op += pitch)
-                        if (i < nrow) *op = make_float2(acc[i], acc[i + 1]);  // (odd H: row H lands in the allocation padding)
+                        if (i < nrow) *op = make_float2(acc[i], (i == il) ? acc_fix : acc[i + 1]);
                 } else {  // last iteration: the caller's [B,C,H,W] tensor, coalesced 128-byte rows
                     float* __restrict__ op = prm.dst + ((size_t)plane * H + yw) * prm.dst_pitch + x;
                     const size_t pitch = (size_t)prm.dst_pitch;
@@ -1070,13 +1080,6 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                     if (lane == 0 && mx != 0u) atomicMax(prm.cls_max + plane, mx);
                 }
             };
-            auto group_sync = [&]() {
-                // immediate barrier ids: with a register id ptxas reserves all 16 named barriers
-                if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(NW * 32) : "memory");
-                else if (grp == 1) asm volatile("bar.sync 3, %0;" ::"n"(NW * 32) : "memory");
-                else if (grp == 2) asm volatile("bar.sync 4, %0;" ::"n"(NW * 32) : "memory");
-                else asm volatile("bar.sync 5, %0;" ::"n"(NW * 32) : "memory");
-            };
             int probe = 0;  // 1: the barriers of this group's next class were already seen complete
 #if PAMR_CPP == 2
             {
@@ -1093,11 +1096,6 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                     PAMR_EV(grp, wq == 0 && lane == 0, 6);
                     float* slot0 = slots + (size_t)(sq0 % NSLOT) * C_::SLOT_FLOATS;
                     float* slot1 = slots + (size_t)(sq1 % NSLOT) * C_::SLOT_FLOATS;
-                    if (border) {  // replicate padding: the group patches the halo rows of its own slots
-                        patch_window<R>(slot0, x0, y0, H, W, wq, lane);
-                        if (two) patch_window<R>(slot1, x0, y0, H, W, wq, lane);
-                        group_sync();
-                    }
                     const int spo = ((wq * R + HALO) / 2) * ROWP + (lane + HALO) * 2;
                     float acc0[R], acc1[R];
 #pragma unroll
@@ -1144,10 +1142,6 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 if (!probe) mbar_wait(smem_u32(&ctrl->tma_bar[bi]), par);  // bytes landed
                 PAMR_EV(grp, wq == 0 && lane == 0, 6);
                 float* slot = slots + (size_t)s * C_::SLOT_FLOATS;
-                if (border) {  // replicate padding: the group patches the halo rows of its own slot
-                    patch_window<R>(slot, x0, y0, H, W, wq, lane);
-                    group_sync();
-                }
                 const float* sp = slot + ((wq * R + HALO) / 2) * ROWP + (lane + HALO) * 2;
                 float acc[R];
 #pragma unroll
@@ -1212,15 +1206,16 @@ __global__ void __launch_bounds__(128) strip_rows_kernel(const Params prm) {
         strip_item(prm, item, lane);
 }
 
-// Copy [planes,H,W] -> row-pair layout [planes,Hp2,Wp,2] (TMA reads 64-bit elements; Wp even keeps its
-// global strides multiples of 16 bytes).  For odd H the second row of the last pair repeats row H-1.
+// Copy [planes,H,W] -> padded row-pair layout [planes,Hpp,Wp,2], Hpp = padded_pairs(H) (TMA reads 64-bit elements; Wp
+// a multiple of 16 keeps its global strides multiples of 16 bytes).  Row pair p holds image rows 2(p - PADP) and
+// 2(p - PADP) + 1, clamped to [0, H-1]: the replicated rows above / below the image and, for odd H, the repeat of row H-1.
 __global__ void __launch_bounds__(128) repack_pairs_kernel(const float* __restrict__ src, float2* __restrict__ dst, int H, int W,
-                                                           int Hp2, int Wp, size_t pair_rows) {
+                                                           int Hpp, int Wp, size_t pair_rows) {
     for (size_t pr = blockIdx.x; pr < pair_rows; pr += gridDim.x) {
-        const size_t plane = pr / Hp2;
-        const int p = (int)(pr % Hp2);
-        const float* __restrict__ s0 = src + (plane * H + 2 * p) * W;
-        const float* __restrict__ s1 = src + (plane * H + min(2 * p + 1, H - 1)) * W;
+        const size_t plane = pr / Hpp;
+        const int p = (int)(pr % Hpp) - PADP;
+        const float* __restrict__ s0 = src + (plane * H + min(max(2 * p, 0), H - 1)) * W;
+        const float* __restrict__ s1 = src + (plane * H + min(max(2 * p + 1, 0), H - 1)) * W;
         float2* __restrict__ d = dst + pr * Wp;
         for (int x = threadIdx.x; x < W; x += blockDim.x) d[x] = make_float2(__ldg(s0 + x), __ldg(s1 + x));
     }
@@ -1279,7 +1274,7 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
                                            (int)C_::SMEM_BYTES));
         if (dev >= 0 && dev < 64) attr_set[dev].store(1, std::memory_order_release);
     }
-    const int Hp2 = (H + 1) / 2, Wt = tiling.Wt, Ht = tiling.Ht;
+    const int Hp2 = padded_pairs(H), Wt = tiling.Wt, Ht = tiling.Ht;
     alignas(64) CUtensorMap tmap;
     int rc = make_tmap(&tmap, src, B * C, Hp2, src_pitch, C_::WIN_H);
     if (rc != PAMR_OK) return rc;
@@ -1439,9 +1434,11 @@ AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
 // pitch (in 64-bit elements) of the row-pair layout for image width W: whole 128-byte lines per row pair, so that
 // the rows TMA fetches and the rows the warps store start on line boundaries for any W
 int pair_pitch(int W) { return (W + 15) / 16 * 16; }
+// row pairs of a plane of the ping-pong buffers, including the replicated pairs above and below the image
+int pair_rows_padded(int H) { return padded_pairs(H); }
 
 int launch_repack_pairs(const float* src, float* dst, int planes, int H, int W, cudaStream_t s) {
-    const int Hp2 = (H + 1) / 2, Wp = pair_pitch(W);
+    const int Hp2 = padded_pairs(H), Wp = pair_pitch(W);
     const size_t pair_rows = (size_t)planes * Hp2;
     const unsigned grid = (unsigned)(pair_rows < 148 * 16 ? pair_rows : 148 * 16);
     repack_pairs_kernel<<<grid, 128, 0, s>>>(src, reinterpret_cast<float2*>(dst), H, W, Hp2, Wp, pair_rows);

@@ -20,6 +20,10 @@ int pair_rows_padded(int H);
 int launch_repack_pairs(const float* src, float* dst, int planes, int H, int W, cudaStream_t s);
 int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, const float* src, float* dst, int dst_pitch,
                            bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int dev, bool dependent, cudaStream_t s);
+bool tuned_fusable(const AffTiling& tiling, int B, int C, int H, int W, int dev);
+size_t tuned_fused_epoch_ints(const AffTiling& tiling, int B);
+int launch_propagate_tuned_fused(const float* aff_tiled, const AffTiling& tiling, const float* buf0, const float* buf1, float* out,
+                                 int B, int C, int H, int W, int iters, unsigned* cls_max, int* epochs, int dev, cudaStream_t s);
 
 namespace {
 
@@ -104,10 +108,10 @@ int launch_generic(const float* aff, const float* src, int src_pitch, float* dst
 }
 
 struct ScratchPlan {
-    size_t pingpong_each, aff_tiled, total;
+    size_t pingpong_each, aff_tiled, epochs, total;
 };
 ScratchPlan plan_scratch(int B, int C, int H, int W, const Dilations& dil, int iters, bool aff_is_tiled) {
-    ScratchPlan p{0, 0, 0};
+    ScratchPlan p{0, 0, 0, 0};
     if (iters <= 0) return p;
     const AffTiling t = tuned_tiling(B, H, W, dil);
     if (t.R > 0) {
@@ -115,10 +119,11 @@ ScratchPlan plan_scratch(int B, int C, int H, int W, const Dilations& dil, int i
         // (TMA reads 64-bit elements and needs 16-byte global strides; whole 128-byte lines per row pair)
         p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * pair_rows_padded(H) * pair_pitch(W) * 2, 256);
         if (!aff_is_tiled) p.aff_tiled = align_up(sizeof(float) * t.floats, 256);
+        p.epochs = align_up(sizeof(int) * tuned_fused_epoch_ints(t, B), 256);  // fused iterations: per-tile / per-image progress
     } else {
         p.pingpong_each = align_up(sizeof(float) * (size_t)B * C * H * W, 256);
     }
-    p.total = 2 * p.pingpong_each + p.aff_tiled;
+    p.total = 2 * p.pingpong_each + p.aff_tiled + p.epochs;
     // small maps: the resident kernel (pamr_resident.cu) carves its own ping-pong buffers + barrier counters out of
     // the same scratch
     int dev = 0;
@@ -271,6 +276,17 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, float* im
     }
     if ((rc = fj.join()) != PAMR_OK) return rc;
 
+#ifdef PAMR_FUSED_ITERATIONS  // experiment build: measured slower than one launch per iteration
+    if (iters >= 2 && tuned_fusable(tiling, B, C, H, W, dev)) {
+        // all iterations in one launch (tile-level dependencies instead of kernel boundaries)
+        int* epochs = (int*)((char*)scratch + 2 * plan.pingpong_each + plan.aff_tiled);
+        const size_t n = tuned_fused_epoch_ints(tiling, B);
+        zero_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((unsigned*)epochs, n);
+        count_launch();
+        PAMR_CUDA_TRY(cudaGetLastError());
+        return launch_propagate_tuned_fused(aff, tiling, P[0], P[1], m_out, B, C, H, W, iters, cls_max, epochs, dev, s);
+    }
+#endif
     const float* src = P[0];
     int next = 1;
     const int Wp = pair_pitch(W);

@@ -266,6 +266,7 @@ struct Ctrl {  // lives in the last CTRL_BYTES of dynamic shared memory
     unsigned long long staged_bar[2 * NSTG];    // the chunk's bytes have landed in the staging ring (chunk n: stage n % NSTG,
                                                 // barrier n % (2 NSTG), so that a barrier's consecutive phases belong to ONE issuer)
     uint32_t tmem_base;
+    int done_cnt[4];                            // fused iterations: compute warps that have stored the tile (by tile visit % 4)
 };
 static_assert(sizeof(Ctrl) <= CTRL_BYTES, "control block");
 
@@ -283,6 +284,18 @@ struct Params {
     int strip_items;               // number of 32-pixel row-strip work items
     int tail_cta0;                 // row strip inside the tile kernel: CTAs >= tail_cta0 (one tile fewer than the
                                    // others) work through the strip_items row items after their last tile; -1: off
+    // ---- fused iterations (tile_epoch != nullptr): ONE launch runs all `iters` propagation steps.  Iteration it reads
+    // buf[it & 1] (tensor map it & 1) and writes buf[(it + 1) & 1], the last one writes `out` / `out_cls_max`.  There is no
+    // grid-wide barrier: a tile of iteration it starts as soon as its 3 x 3 tile neighbourhood (and, for a bottom-row
+    // tile, the image's row strip) of iteration it - 1 is complete, tracked in tile_epoch / strip_count.
+    int iters;
+    const float* buf[2];
+    float* out;
+    unsigned* out_cls_max;
+    int out_pitch;
+    int* tile_epoch;               // [ntiles] iterations completed per tile (zeroed before the launch)
+    int* strip_count;              // [B] row-strip items completed per image, over all iterations
+    int strip_items_per_image;
 #ifdef PAMR_EXPERIMENTS
     long long* dbg;                // timeline buffer [5 streams][4096][2] = {clock64, code} or nullptr (tools/timeline.py)
     int dbg_cta;
@@ -318,18 +331,51 @@ __host__ __device__ __forceinline__ size_t plane_index(int pitch, int y, int x) 
     return ((size_t)((y + HALO) >> 1) * pitch + x) * 2 + ((y + HALO) & 1);
 }
 __device__ __forceinline__ size_t src_plane_stride(const Params& p) { return (size_t)p.Hp2 * p.src_pitch * 2; }
-__device__ __forceinline__ float* dst_pixel(const Params& p, int plane, int y, int x) {
-    return p.dst_pair ? p.dst + (size_t)plane * p.Hp2 * p.dst_pitch * 2 + plane_index(p.dst_pitch, y, x)
-                      : p.dst + ((size_t)plane * p.H + y) * p.dst_pitch + x;
+// what one iteration reads and writes
+struct IterIO {
+    const float* src;
+    float* dst;
+    unsigned* cls_max;
+    int dst_pitch, dst_pair;
+};
+template <bool FUSED>
+__device__ __forceinline__ IterIO iter_io(const Params& p, int it) {
+    IterIO io;
+    if (!FUSED) {  // plain launch: one iteration
+        io.src = p.src; io.dst = p.dst; io.cls_max = p.cls_max; io.dst_pitch = p.dst_pitch; io.dst_pair = p.dst_pair;
+    } else {
+        const bool last = it == p.iters - 1;
+        io.src = p.buf[it & 1];
+        io.dst = last ? p.out : const_cast<float*>(p.buf[(it + 1) & 1]);
+        io.cls_max = last ? p.out_cls_max : nullptr;
+        io.dst_pitch = last ? p.out_pitch : p.src_pitch;
+        io.dst_pair = last ? 0 : 1;
+    }
+    return io;
+}
+__device__ __forceinline__ float* dst_pixel(const Params& p, const IterIO& io, int plane, int y, int x) {
+    return io.dst_pair ? io.dst + (size_t)plane * p.Hp2 * io.dst_pitch * 2 + plane_index(io.dst_pitch, y, x)
+                       : io.dst + ((size_t)plane * p.H + y) * io.dst_pitch + x;
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spins until *p >= target (another CTA's release); a wait that never ends is a protocol bug: trap instead of hanging
+__device__ __forceinline__ void wait_at_least(const int* p, int target) {
+    unsigned spins = 0;
+    while (ld_acquire(p) < target)
+        if (++spins > (1u << 26)) __trap();
 }
 // rows beyond the image that repeat row y (y == 0: the 24 rows above; y == H-1: the rows below, including the second
 // half of the last row pair when H is odd); none for any other row
-__device__ __forceinline__ void store_replicas(const Params& p, int plane, int y, int x, float v) {
-    if (!p.dst_pair) return;
+__device__ __forceinline__ void store_replicas(const Params& p, const IterIO& io, int plane, int y, int x, float v) {
+    if (!io.dst_pair) return;
     if (y == 0)
-        for (int r = -HALO; r < 0; ++r) *dst_pixel(p, plane, r, x) = v;
+        for (int r = -HALO; r < 0; ++r) *dst_pixel(p, io, plane, r, x) = v;
     if (y == p.H - 1)
-        for (int r = p.H; r < 2 * (((p.H + 1) >> 1)) + HALO; ++r) *dst_pixel(p, plane, r, x) = v;
+        for (int r = p.H; r < 2 * (((p.H + 1) >> 1)) + HALO; ++r) *dst_pixel(p, io, plane, r, x) = v;
 }
 
 // ---------------------------------------------------------------- TMEM weight layout
@@ -726,7 +772,8 @@ __device__ __forceinline__ void compute_pass2(const float* __restrict__ sp0, con
 // pixel per lane, neighbours straight from global memory / L2 with clamped coordinates, weights from the
 // row-strip region of the affinity layout: coalesced).  The strip spans ALL columns, including its corner with
 // the column strip.
-__device__ __forceinline__ void strip_item(const Params& prm, int item, int lane) {
+template <bool FUSED>
+__device__ __forceinline__ void strip_item(const Params& prm, const IterIO& io, int it, int item, int lane) {
     const int C = prm.C, H = prm.H, W = prm.W;
     const int hrows = H - prm.Ht, xblocks = (W + 31) / 32;
     const int per_plane = hrows * xblocks;
@@ -735,7 +782,17 @@ __device__ __forceinline__ void strip_item(const Params& prm, int item, int lane
     const bool valid = x < W;
     const int xc = min(x, W - 1);
     const int b = plane / C;
-    const float* __restrict__ pl = prm.src + (size_t)plane * src_plane_stride(prm);
+    if (FUSED && it > 0) {
+        // fused iterations: the item reads rows >= Ht - 24 of iteration it - 1 (and overwrites what iteration it - 1 read
+        // there): the image's bottom tile row and its row strip of that iteration must be complete
+        if (lane == 0) {
+            const int t0 = (b * prm.tiles_y + prm.tiles_y - 1) * prm.tiles_x;
+            for (int tx = 0; tx < prm.tiles_x; ++tx) wait_at_least(prm.tile_epoch + t0 + tx, it);
+            wait_at_least(prm.strip_count + b, it * prm.strip_items_per_image);
+        }
+        __syncwarp();
+    }
+    const float* __restrict__ pl = io.src + (size_t)plane * src_plane_stride(prm);
     const float* __restrict__ wp = prm.aff + prm.rs_base + ((size_t)b * hrows + yi) * 48 * W + xc;
     float acc = 0.f;  // one FMA chain in tap-sequence order: bit-identical to the tile kernel's result
 #pragma unroll
@@ -746,12 +803,17 @@ __device__ __forceinline__ void strip_item(const Params& prm, int item, int lane
         acc = fmaf(__ldg(wp + (size_t)s * W), __ldg(pl + plane_index(prm.src_pitch, yy, xx)), acc);
     }
     if (valid) {
-        *dst_pixel(prm, plane, y, x) = acc;
-        store_replicas(prm, plane, y, x, acc);
+        *dst_pixel(prm, io, plane, y, x) = acc;
+        store_replicas(prm, io, plane, y, x, acc);
     }
-    if (prm.cls_max != nullptr) {
+    if (io.cls_max != nullptr) {
         const unsigned m = __reduce_max_sync(0xffffffffu, valid ? ordered_from_float(acc) : 0u);
-        if (lane == 0 && m != 0u) atomicMax(prm.cls_max + plane, m);
+        if (lane == 0 && m != 0u) atomicMax(io.cls_max + plane, m);
+    }
+    if (FUSED) {  // this item of iteration `it` is stored
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(prm.strip_count + b) : "memory");
     }
 }
 
@@ -789,8 +851,8 @@ __constant__ CsOffsets c_cs = make_cs_offsets();
 #define PAMR_CS_INLINE __forceinline__
 #endif
 template <int R>
-__device__ PAMR_CS_INLINE void column_strip_pass(const Params& prm, const float* __restrict__ slot, uint32_t tbase, int plane,
-                                                  int y0, int wq, int lane) {
+__device__ PAMR_CS_INLINE void column_strip_pass(const Params& prm, const IterIO& io, const float* __restrict__ slot, uint32_t tbase,
+                                                  int plane, int y0, int wq, int lane) {
     constexpr int LP = Cfg<R>::CS_LP, TPL = Cfg<R>::CS_TPL;
     const int part = lane % LP, i = min(lane / LP, R - 1);
     const bool active = lane < R * LP;
@@ -817,18 +879,40 @@ __device__ PAMR_CS_INLINE void column_strip_pass(const Params& prm, const float*
     const int y = y0 + row;
     const bool valid = active && part == LP - 1 && y < prm.H;
     if (valid) {
-        *dst_pixel(prm, plane, y, prm.Wt) = acc;
-        store_replicas(prm, plane, y, prm.Wt, acc);
+        *dst_pixel(prm, io, plane, y, prm.Wt) = acc;
+        store_replicas(prm, io, plane, y, prm.Wt, acc);
     }
-    if (prm.cls_max != nullptr) {
+    if (io.cls_max != nullptr) {
         const unsigned m = __reduce_max_sync(0xffffffffu, valid ? ordered_from_float(acc) : 0u);
-        if (lane == 0 && m != 0u) atomicMax(prm.cls_max + plane, m);
+        if (lane == 0 && m != 0u) atomicMax(io.cls_max + plane, m);
     }
 }
 
-template <int R>
+// The schedule of one CTA: tile visits (iteration it, slot ti) in order.  In iteration it the CTA plays the role of
+// "virtual CTA" v = (blockIdx.x + it * rot) % grid and takes the tiles v, v + grid, v + 2 grid, ...: the roles with one
+// tile more than the others rotate over the CTAs (rot = number of short roles), so that a fused launch gives every CTA
+// the same work over its iterations.  Plain launch: one iteration, v = blockIdx.x.
+struct Visit {
+    int it, ti, v, mt;  // iteration, tile slot in the iteration, virtual CTA index, tiles of this iteration
+    int cta, grid, rot, ntiles;
+    __device__ __forceinline__ int tiles_of(int vv) const { return (ntiles - vv + grid - 1) / grid; }
+    __device__ __forceinline__ void start(int cta_, int grid_, int rot_, int ntiles_) {
+        cta = cta_; grid = grid_; rot = rot_; ntiles = ntiles_;
+        it = 0; ti = 0; v = cta; mt = tiles_of(v);
+    }
+    __device__ __forceinline__ void next() {
+        if (++ti == mt) {
+            ti = 0; ++it;
+            v = (cta + it * rot) % grid;
+            mt = tiles_of(v);
+        }
+    }
+    __device__ __forceinline__ int tile() const { return v + ti * grid; }
+};
+
+template <int R, bool FUSED>
 __global__ void __launch_bounds__(NTHREADS, 1)
-propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params prm) {
+propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap1, const Params prm) {
     using C_ = Cfg<R>;
     using L = TmemLayout<R>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -854,6 +938,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         mbar_init(smem_u32(&ctrl->csw_staged_bar), 1);
         mbar_init(smem_u32(&ctrl->csw_full_bar), 1);
         mbar_init(smem_u32(&ctrl->csw_free_bar), NW * active_groups);
+        ctrl->done_cnt[0] = ctrl->done_cnt[1] = ctrl->done_cnt[2] = ctrl->done_cnt[3] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -869,12 +954,19 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
     // (griddepcontrol.wait below) before it reads the class planes.  Both instructions are no-ops in a plain launch.
     asm volatile("griddepcontrol.launch_dependents;");
 
-    const int my_tiles = (prm.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int tiles_per_img = prm.tiles_x * prm.tiles_y;
+    // Tile visits of this CTA (struct Visit): gt counts them over all iterations of the launch (one iteration in a plain
+    // launch).  Every ring, barrier phase and counter below runs on gt, so that iteration it + 1 follows iteration it
+    // like one more tile: no cold start, no tail.
+    constexpr bool fused = FUSED;
+    const int n_iters = fused ? prm.iters : 1;
+    const int rot = (fused && prm.ntiles > (int)gridDim.x) ? ((int)gridDim.x - prm.ntiles % (int)gridDim.x) % (int)gridDim.x : 0;
+    int GT = 0;
+    for (int i = 0; i < n_iters; ++i)
+        GT += (prm.ntiles - ((int)blockIdx.x + i * rot) % (int)gridDim.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     // tile-major affinity layout: the 48*R*128 weights of a tile are one contiguous block
-    auto tile_weights = [&](int ti) -> const float* {
-        const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+    auto tile_weights = [&](int tile) -> const float* {
         const int b = tile / tiles_per_img, t = tile % tiles_per_img;
         return prm.aff + (((size_t)b * prm.tiles_y + t / prm.tiles_x) * prm.tiles_x + t % prm.tiles_x) * aff_tile_floats(R);
     };
@@ -884,17 +976,41 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         // Sequence number n = (tile_iter, class) -> slot n % NSLOT, barrier pair n % NBAR.  A consumer
         // group waits for tma_bar (bytes landed), computes, and releases the slot through empty_bar; the producer may refill slot
         // n % NSLOT once sequence number n - NSLOT has been released.
-        const long long total = (long long)my_tiles * C;
+        const long long total = (long long)GT * C;
         [[maybe_unused]] int ev_n = 0;
         // the class planes are the previous iteration's output (and this iteration's stores go to the buffer the previous
         // one reads: every store depends on a plane that is loaded after this wait)
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        for (long long n_issue = 0; n_issue < total; ++n_issue) {
+        Visit vis;
+        vis.start((int)blockIdx.x, (int)gridDim.x, rot, prm.ntiles);
+        int c = 0, gt = 0;
+        for (long long n_issue = 0; n_issue < total; ++n_issue, ++c) {
+            if (c == C) { c = 0; ++gt; vis.next(); }
             const int s = (int)(n_issue % NSLOT), bi = (int)(n_issue % NBAR);
-            const int ti = (int)(n_issue / C), c = (int)(n_issue % C);
-            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int it = vis.it;
+            const int tile = vis.tile();
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
             const int x0 = (t % prm.tiles_x) * TX, y0 = (t / prm.tiles_x) * C_::TY;
+            const CUtensorMap* tm = (fused && (it & 1)) ? &tmap1 : &tmap;
+            if (fused && it > 0 && c == 0) {
+                // Fused iterations: this tile reads a 24-pixel halo of iteration it - 1, and its stores overwrite what
+                // iteration it - 1 read there: the tiles around it (same image) must have finished that iteration --
+                // and, under a bottom-row tile, the image's row strip.  Lanes 0..8 watch one neighbour each, lane 9 the
+                // strip (one L2 round trip for all of them instead of ten in a row).
+                const int tx = t % prm.tiles_x, ty = t / prm.tiles_x;
+                const int* flag = nullptr;
+                int target = it;
+                if (lane < 9) {
+                    const int nx = tx + lane % 3 - 1, ny = ty + lane / 3 - 1;
+                    if (nx >= 0 && nx < prm.tiles_x && ny >= 0 && ny < prm.tiles_y) flag = prm.tile_epoch + b * tiles_per_img + ny * prm.tiles_x + nx;
+                } else if (lane == 9 && prm.strip_items_per_image > 0 && ty == prm.tiles_y - 1) {
+                    flag = prm.strip_count + b;
+                    target = it * prm.strip_items_per_image;
+                }
+                if (flag != nullptr) wait_at_least(flag, target);
+                __syncwarp();
+                asm volatile("fence.proxy.async;" ::: "memory");  // TMA (async proxy) reads what the other CTAs stored
+            }
             if (lane == 0) {
                 if (n_issue >= NSLOT) {  // the previous occupant of this slot has been consumed
                     const long long prev = n_issue - NSLOT;
@@ -904,11 +1020,11 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive_expect_tx(bar, C_::SLOT_BYTES);
                 // 64-bit elements = row pairs: coordinates (column, row pair, plane)
-                tma_load_3d(smem_u32(slots + (size_t)s * C_::SLOT_FLOATS), &tmap, bar, x0 - HALO, y0 / 2, b * C + c);  // (y0 - HALO) / 2 + PADP
+                tma_load_3d(smem_u32(slots + (size_t)s * C_::SLOT_FLOATS), tm, bar, x0 - HALO, y0 / 2, b * C + c);  // (y0 - HALO) / 2 + PADP
                 if (PF_PLANES > 0 && n_issue + PF_PLANES < total) {  // pull a later plane window from HBM into L2
                     const long long np = n_issue + PF_PLANES;
-                    const int pti = (int)(np / C), pc = (int)(np % C);
-                    const int ptile = (int)blockIdx.x + pti * (int)gridDim.x;
+                    const int pc = (int)(np % C);
+                    const int ptile = tile;  // (experiment knob: same tile only)
                     const int pb = ptile / tiles_per_img, pt = ptile % tiles_per_img;
                     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
                                  ::"l"(&tmap), "r"((pt % prm.tiles_x) * TX - HALO), "r"(((pt / prm.tiles_x) * C_::TY) / 2), "r"(pb * C + pc)
@@ -919,8 +1035,10 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             // per lane quarter of the tile-major layout) from HBM into L2, one quarter per class, so that
             // the fill warps' loads hit L2.
             const int pq = c - prm.pf_class;
-            if (pq >= 0 && pq < 4 && ti + 1 < my_tiles && lane == 0) {
-                const float* wp = tile_weights(ti + 1) + (size_t)pq * (12 * R * 128);
+            if (pq >= 0 && pq < 4 && gt + 1 < GT && lane == 0) {
+                Visit nv = vis;
+                nv.next();
+                const float* wp = tile_weights(nv.tile()) + (size_t)pq * (12 * R * 128);
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wp), "r"(12 * R * 128 * 4) : "memory");
             }
             __syncwarp();
@@ -932,13 +1050,16 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         // reports.  (A control thread on a saturated SM pays a few hundred cycles per mbarrier round trip, hence
         // 32 KB per loop iteration.)
         if (lane == 0) {
-            const int total = my_tiles * L::NCH;
+            const int total = GT * L::NCH;
             [[maybe_unused]] int ev_n = 0;
             int cs_uses = 0;  // border tiles of this CTA so far
+            Visit vis;
+            vis.start((int)blockIdx.x, (int)gridDim.x, rot, prm.ntiles);
             for (int n = 0; n < total; ++n) {
-                const int ti = n / L::NCH, c = n % L::NCH, g = n % NSTG;
+                const int c = n % L::NCH, g = n % NSTG;
+                if (c == 0 && n > 0) vis.next();
+                const int tile = vis.tile();
                 if (c == 0 && wc > 0) {  // a tile on the right image border: its column-strip weights -> shared memory
-                    const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
                     const int b = tile / tiles_per_img, t = tile % tiles_per_img;
                     if (t % prm.tiles_x == prm.tiles_x - 1) {
                         if (cs_uses > 0) mbar_wait(smem_u32(&ctrl->csw_full_bar), (uint32_t)(cs_uses - 1) & 1u);  // the staging area has been read
@@ -957,7 +1078,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 const uint32_t bar = smem_u32(&ctrl->staged_bar[n % (2 * NSTG)]);
                 mbar_arrive_expect_tx(bar, units * UNIT_BYTES);
                 bulk_load(smem_u32(stage_ring + (size_t)g * (CHUNK_UNITS * UNIT_BYTES)),
-                          tile_weights(ti) + (size_t)c * (CHUNK_UNITS * UNIT * 128), units * UNIT_BYTES, bar);
+                          tile_weights(tile) + (size_t)c * (CHUNK_UNITS * UNIT * 128), units * UNIT_BYTES, bar);
                 PAMR_EV(3, true, 2000 + c);
             }
         }
@@ -965,7 +1086,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         // ===================== weight issuers: staging ring -> TMEM with tcgen05.cp =====================
         // two control threads (warps 14 and 15) take the even and the odd chunks of the stream
         if (lane == 0) {
-            const int total = my_tiles * L::NCH;
+            const int total = GT * L::NCH;
             const uint32_t tb = ctrl->tmem_base;
             [[maybe_unused]] int ev_n = 0;
             int n = warp - W_ISSUER;
@@ -976,10 +1097,14 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
             static_assert(L::NCH % 2 == 0 || NSTG < L::NCH, "the issuers must stay less than a tile apart");
             if (n < total) mbar_wait(smem_u32(&ctrl->staged_bar[n % (2 * NSTG)]), (uint32_t)(n / (2 * NSTG)) & 1u);  // bytes landed
             int cs_uses = 0;  // border tiles of this CTA so far
+            Visit vis;
+            vis.start((int)blockIdx.x, (int)gridDim.x, rot, prm.ntiles);
+            int vgt = 0;
             for (; n < total; n += 2) {
-                const int ti = n / L::NCH, c = n % L::NCH, g = n % NSTG;
+                const int gt = n / L::NCH, c = n % L::NCH, g = n % NSTG;
+                while (vgt < gt) { vis.next(); ++vgt; }
                 if (c == 0 && wc > 0) {  // (chunk 0 always meets issuer 0) a border tile: its strip weights -> spare TMEM columns
-                    const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                    const int tile = vis.tile();
                     if ((tile % tiles_per_img) % prm.tiles_x == prm.tiles_x - 1) {
                         mbar_wait(smem_u32(&ctrl->csw_staged_bar), (uint32_t)cs_uses & 1u);
                         if (cs_uses > 0) mbar_wait(smem_u32(&ctrl->csw_free_bar), (uint32_t)(cs_uses - 1) & 1u);  // previous border tile done
@@ -992,7 +1117,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                         ++cs_uses;
                     }
                 }
-                if (ti > 0) mbar_wait(smem_u32(&ctrl->free_bar[c]), (uint32_t)(ti - 1) & 1u);  // the previous tile's last passes have read the chunk
+                if (gt > 0) mbar_wait(smem_u32(&ctrl->free_bar[c]), (uint32_t)(gt - 1) & 1u);  // the previous tile's last passes have read the chunk
                 tc_fence_after();
                 PAMR_EV(4, warp == W_ISSUER, 2100 + c);
                 const int units = min(CHUNK_UNITS, L::NU - c * CHUNK_UNITS);
@@ -1012,13 +1137,46 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
         const uint32_t filled0 = smem_u32(&ctrl->filled_bar[0]), free0 = smem_u32(&ctrl->free_bar[0]);
         int cs_seen = 0;  // border tiles of this CTA so far
         [[maybe_unused]] int ev_n = 0;
-        for (int ti = 0; ti < my_tiles; ++ti) {
-            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+        // Fused iterations: a finished tile is announced (epoch in global memory) one class pass LATE, when the warp's
+        // stores have long drained and the fences that order them before the announcement cost nothing; issued right
+        // after the stores they would wait ~2 k cycles per tile.  Each warp orders its stores before its count at CTA
+        // scope; the warp that completes the count pays the one gpu-scope fence and publishes the epoch (the
+        // block-barrier + one-thread-fence idiom of a grid-wide barrier, per tile).
+        int pend_tile = -1, pend_it = 0, pend_slot = 0;
+        auto announce = [&]() {
+            if (pend_tile < 0) return;
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("fence.acq_rel.cta;" ::: "memory");
+                const int old = atomicAdd(&ctrl->done_cnt[pend_slot], 1);
+                if (old == NW * active_groups - 1) {
+                    ctrl->done_cnt[pend_slot] = 0;  // (the groups are never two tiles apart: the slot is not in use again yet)
+                    __threadfence();
+                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(prm.tile_epoch + pend_tile), "r"(pend_it + 1) : "memory");
+                }
+            }
+            pend_tile = -1;
+        };
+        Visit vis;
+        vis.start((int)blockIdx.x, (int)gridDim.x, rot, prm.ntiles);
+        for (int gt = 0; gt < GT; ++gt, vis.next()) {
+            const int it = vis.it, ti = vis.ti;
+            const int tile = vis.tile();
+            // ---- row strip y in [Ht,H): the roles that own one tile fewer than the others take it.  In a plain launch
+            //      after their last tile (they would idle in the last wave); in a fused launch BEFORE their first tile of
+            //      the iteration: the strip of iteration it depends on iteration it - 1 only, and the bottom tiles of
+            //      iteration it + 1 wait for it
+            if (fused && ti == 0 && prm.tail_cta0 >= 0 && vis.v >= prm.tail_cta0) {
+                announce();  // (the strip may wait for the very tile this warp has not announced yet)
+                const int nw = ((int)gridDim.x - prm.tail_cta0) * NWC;
+                for (int item = (vis.v - prm.tail_cta0) * NWC + warp; item < prm.strip_items; item += nw)
+                    strip_item<FUSED>(prm, iter_io<FUSED>(prm, it), it, item, lane);
+            }
             const int b = tile / tiles_per_img, t = tile % tiles_per_img;
             const int x0 = (t % prm.tiles_x) * TX, y0 = (t / prm.tiles_x) * C_::TY;
             const int x = x0 + lane, yw = y0 + wq * R;
             const bool xok = x < W;
-            const long long seq0 = (long long)ti * C;
+            const long long seq0 = (long long)gt * C;
             const int nrow = xok ? max(0, min(R, H - yw)) : 0;  // rows of this thread inside the image
             const bool cs_tile = wc > 0 && (t % prm.tiles_x == prm.tiles_x - 1);  // this tile also computes the column strip
             if (cs_tile && grp < active_groups) {
@@ -1029,12 +1187,13 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
 
             // ---- store of one class plane's results (+ optional class max)
             auto store_plane = [&](int k, const float (&acc)[R]) {
+                const IterIO io = iter_io<FUSED>(prm, it);  // (derived here, not held across the pass: the pass needs every register)
                 const int plane = b * C + k;
                 [[maybe_unused]] float acc_fix = 0.f;
-                if (prm.dst_pair) {  // row pairs: 8-byte stores, 256 contiguous bytes per warp
-                    float2* __restrict__ op = reinterpret_cast<float2*>(prm.dst) +
-                                              ((size_t)plane * prm.Hp2 + PADP + (yw >> 1)) * prm.dst_pitch + x;
-                    const size_t pitch = (size_t)prm.dst_pitch;
+                if (io.dst_pair) {  // row pairs: 8-byte stores, 256 contiguous bytes per warp
+                    float2* __restrict__ op = reinterpret_cast<float2*>(io.dst) +
+                                              ((size_t)plane * prm.Hp2 + PADP + (yw >> 1)) * io.dst_pitch + x;
+                    const size_t pitch = (size_t)io.dst_pitch;
                     // replicate padding as data: the owner of row 0 / row H-1 also fills the 24 rows beyond it (a warp-uniform
                     // case: only the first warp of the top tiles and the warp that holds row H-1)
                     const int il = H - 1 - yw;  // index of row H-1 in this thread's strip, if it is there
@@ -1060,8 +1219,8 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                     for (int i = 0; i < R; i += 2, op += pitch)
                         if (i < nrow) *op = make_float2(acc[i], (i == il) ? acc_fix : acc[i + 1]);
                 } else {  // last iteration: the caller's [B,C,H,W] tensor, coalesced 128-byte rows
-                    float* __restrict__ op = prm.dst + ((size_t)plane * H + yw) * prm.dst_pitch + x;
-                    const size_t pitch = (size_t)prm.dst_pitch;
+                    float* __restrict__ op = io.dst + ((size_t)plane * H + yw) * io.dst_pitch + x;
+                    const size_t pitch = (size_t)io.dst_pitch;
                     if (nrow == R) {
 #pragma unroll
                         for (int i = 0; i < R; ++i, op += pitch) *op = acc[i];
@@ -1071,13 +1230,13 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                             if (i < nrow) *op = acc[i];
                     }
                 }
-                if (prm.cls_max != nullptr) {  // last iteration only: keep its ALU work out of the other nine
+                if (io.cls_max != nullptr) {  // last iteration only: keep its ALU work out of the other nine
                     unsigned mx = 0u;
 #pragma unroll
                     for (int i = 0; i < R; ++i)
                         if (i < nrow) mx = max(mx, ordered_from_float(acc[i]));
                     mx = __reduce_max_sync(0xffffffffu, mx);
-                    if (lane == 0 && mx != 0u) atomicMax(prm.cls_max + plane, mx);
+                    if (lane == 0 && mx != 0u) atomicMax(io.cls_max + plane, mx);
                 }
             };
             int probe = 0;  // 1: the barriers of this group's next class were already seen complete
@@ -1106,10 +1265,10 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                     const bool first = (pp == grp), last = (pp + NG >= npairs);
 #endif
                     compute_pass2<R>(slot0 + spo, slot1 + spo, two, tbase, acc0, acc1, x, W, first ? filled0 : 0u, last ? free0 : 0u,
-                                     (uint32_t)ti & 1u, lane);
+                                     (uint32_t)gt & 1u, lane);
                     if (cs_tile) {
-                        column_strip_pass<R>(prm, slot0, tbase, b * C + k0, y0, wq, lane);
-                        if (two) column_strip_pass<R>(prm, slot1, tbase, b * C + k1, y0, wq, lane);
+                        column_strip_pass<R>(prm, iter_io<FUSED>(prm, it), slot0, tbase, b * C + k0, y0, wq, lane);
+                        if (two) column_strip_pass<R>(prm, iter_io<FUSED>(prm, it), slot1, tbase, b * C + k1, y0, wq, lane);
                         if (last) {  // this warp is done with the tile's strip weights
                             tc_fence_before();
                             __syncwarp();
@@ -1129,6 +1288,7 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                     }
                     store_plane(k0, acc0);
                     if (two) store_plane(k1, acc1);
+                    if (fused && first) announce();  // the previous tile of this warp
                     PAMR_EV(grp, wq == 0 && lane == 0, 8);
                 }
             }
@@ -1152,15 +1312,15 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                 const bool first = (k == grp), last = (k + NG >= C);
 #endif
 #ifdef PAMR_PASS_SPECIALISED
-                if (first && last) compute_pass<R, true, true>(sp, tbase, acc, x, W, filled0, free0, (uint32_t)ti & 1u, lane);
-                else if (first) compute_pass<R, true, false>(sp, tbase, acc, x, W, filled0, free0, (uint32_t)ti & 1u, lane);
-                else if (last) compute_pass<R, false, true>(sp, tbase, acc, x, W, filled0, free0, (uint32_t)ti & 1u, lane);
-                else compute_pass<R, false, false>(sp, tbase, acc, x, W, filled0, free0, (uint32_t)ti & 1u, lane);
+                if (first && last) compute_pass<R, true, true>(sp, tbase, acc, x, W, filled0, free0, (uint32_t)gt & 1u, lane);
+                else if (first) compute_pass<R, true, false>(sp, tbase, acc, x, W, filled0, free0, (uint32_t)gt & 1u, lane);
+                else if (last) compute_pass<R, false, true>(sp, tbase, acc, x, W, filled0, free0, (uint32_t)gt & 1u, lane);
+                else compute_pass<R, false, false>(sp, tbase, acc, x, W, filled0, free0, (uint32_t)gt & 1u, lane);
 #else
-                compute_pass<R>(sp, tbase, acc, x, W, first ? filled0 : 0u, last ? free0 : 0u, (uint32_t)ti & 1u, lane);
+                compute_pass<R>(sp, tbase, acc, x, W, first ? filled0 : 0u, last ? free0 : 0u, (uint32_t)gt & 1u, lane);
 #endif
                 if (cs_tile) {
-                    column_strip_pass<R>(prm, slot, tbase, b * C + k, y0, wq, lane);
+                    column_strip_pass<R>(prm, iter_io<FUSED>(prm, it), slot, tbase, b * C + k, y0, wq, lane);
                     if (last) {  // this warp is done with the tile's strip weights
                         tc_fence_before();
                         __syncwarp();
@@ -1179,18 +1339,23 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
                     probe = (int)mbar_poll(smem_u32(&ctrl->tma_bar[sq2 % NBAR]), (uint32_t)(sq2 / NBAR) & 1u);
                 }
                 store_plane(k, acc);
+                if (fused && first) announce();  // the previous tile of this warp
                 PAMR_EV(grp, wq == 0 && lane == 0, 8);
             }
             }
 #endif
+            if (fused && grp < active_groups) {  // this warp has stored its share of the tile: tell the others -- later (below)
+                pend_tile = tile;
+                pend_it = it;
+                pend_slot = gt & 3;
+            }
+            if (!fused && ti == vis.mt - 1 && prm.tail_cta0 >= 0 && (int)blockIdx.x >= prm.tail_cta0) {
+                const int nw = ((int)gridDim.x - prm.tail_cta0) * NWC;
+                for (int item = ((int)blockIdx.x - prm.tail_cta0) * NWC + warp; item < prm.strip_items; item += nw)
+                    strip_item<FUSED>(prm, iter_io<FUSED>(prm, it), it, item, lane);
+            }
         }
-        // ---- row strip in the tail: the CTAs that own one tile fewer than the rest would idle during
-        //      the last wave; they compute the row strip y in [Ht,H) instead (no separate launch)
-        if (prm.tail_cta0 >= 0 && (int)blockIdx.x >= prm.tail_cta0) {
-            const int nw = ((int)gridDim.x - prm.tail_cta0) * NWC;
-            for (int item = ((int)blockIdx.x - prm.tail_cta0) * NWC + warp; item < prm.strip_items; item += nw)
-                strip_item(prm, item, lane);
-        }
+        if (fused) announce();
     }
 
     tc_fence_before();
@@ -1202,8 +1367,9 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const Params pr
 // Row strip as a launch of its own: only when the tile kernel's last wave has no idle CTAs for it.
 __global__ void __launch_bounds__(128) strip_rows_kernel(const Params prm) {
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const IterIO io = iter_io<false>(prm, 0);
     for (int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < prm.strip_items; item += gridDim.x * wpb)
-        strip_item(prm, item, lane);
+        strip_item<false>(prm, io, 0, item, lane);
 }
 
 // Copy [planes,H,W] -> padded row-pair layout [planes,Hpp,Wp,2], Hpp = padded_pairs(H) (TMA reads 64-bit elements; Wp
@@ -1263,21 +1429,34 @@ inline bool row_strip_in_tail(long long items, long long ntiles, int grid) {
     return (items + warps - 1) / warps <= TAIL_ITEMS_MAX;
 }
 
+// fused: nullptr (one iteration src -> dst) or the description of a launch that runs all iterations
+struct FusedArgs {
+    int iters;
+    const float* buf0;
+    const float* buf1;
+    int* epochs;  // [ntiles + B] zeroed ints
+};
 template <int R>
 int launch_one(const float* aff, const AffTiling& tiling, const float* src, int src_pitch, float* dst, int dst_pitch,
-               bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int sm_count, int dev, bool dependent, cudaStream_t s) {
+               bool dst_pair, int B, int C, int H, int W, unsigned* cls_max, int sm_count, int dev, bool dependent,
+               const FusedArgs* fused, cudaStream_t s) {
     using C_ = Cfg<R>;
     // function attributes are per device: set once per (kernel, device)
     static std::atomic<int> attr_set[64];
     if (dev < 0 || dev >= 64 || attr_set[dev].load(std::memory_order_acquire) == 0) {
-        PAMR_CUDA_TRY(cudaFuncSetAttribute(propagate_sm100_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PAMR_CUDA_TRY(cudaFuncSetAttribute(propagate_sm100_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)C_::SMEM_BYTES));
+#ifdef PAMR_FUSED_ITERATIONS
+        PAMR_CUDA_TRY(cudaFuncSetAttribute(propagate_sm100_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)C_::SMEM_BYTES));
+#endif
         if (dev >= 0 && dev < 64) attr_set[dev].store(1, std::memory_order_release);
     }
     const int Hp2 = padded_pairs(H), Wt = tiling.Wt, Ht = tiling.Ht;
-    alignas(64) CUtensorMap tmap;
-    int rc = make_tmap(&tmap, src, B * C, Hp2, src_pitch, C_::WIN_H);
+    alignas(64) CUtensorMap tmap, tmap1;
+    int rc = make_tmap(&tmap, fused ? fused->buf0 : src, B * C, Hp2, src_pitch, C_::WIN_H);
     if (rc != PAMR_OK) return rc;
+    if ((rc = make_tmap(&tmap1, fused ? fused->buf1 : src, B * C, Hp2, src_pitch, C_::WIN_H)) != PAMR_OK) return rc;
     Params p;
     p.aff = aff; p.src = src; p.dst = dst; p.cls_max = cls_max;
     p.src_pitch = src_pitch; p.dst_pitch = dst_pitch; p.dst_pair = dst_pair ? 1 : 0; p.Hp2 = Hp2;
@@ -1289,6 +1468,8 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
     p.cs_base = tiling.cs_base; p.rs_base = tiling.rs_base;
     p.strip_items = 0;
     p.tail_cta0 = -1;
+    p.iters = 1; p.buf[0] = p.buf[1] = nullptr; p.out = nullptr; p.out_cls_max = nullptr; p.out_pitch = 0;
+    p.tile_epoch = nullptr; p.strip_count = nullptr; p.strip_items_per_image = 0;
 #ifdef PAMR_EXPERIMENTS
     p.dbg = nullptr;
     p.dbg_cta = g_timeline_cta.load(std::memory_order_relaxed);
@@ -1300,6 +1481,17 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
     const int grid = p.ntiles < sm_count ? p.ntiles : sm_count;
     const long long row_items = (long long)B * C * (H - Ht) * ((W + 31) / 32);
     if (row_items > 0x7fffffffLL) return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: row strip too large");
+    if (fused != nullptr) {
+        if (Ht < H && !row_strip_in_tail(row_items, ntiles, grid))
+            return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: fused launch needs the row strip in the tail");
+        p.iters = fused->iters;
+        p.buf[0] = fused->buf0; p.buf[1] = fused->buf1;
+        p.out = dst; p.out_cls_max = cls_max; p.out_pitch = dst_pitch;
+        p.src = nullptr; p.dst = nullptr; p.cls_max = nullptr;
+        p.tile_epoch = fused->epochs;
+        p.strip_count = fused->epochs + p.ntiles;
+        p.strip_items_per_image = (int)(row_items / B);
+    }
     if (Ht < H && row_strip_in_tail(row_items, ntiles, grid)) {
         p.strip_items = (int)row_items;  // the tile kernel's short CTAs do the row strip
         p.tail_cta0 = p.ntiles % grid;
@@ -1326,9 +1518,15 @@ int launch_one(const float* aff, const AffTiling& tiling, const float* src, int 
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        PAMR_CUDA_TRY(cudaLaunchKernelEx(&cfg, propagate_sm100_kernel<R>, tmap, p));
+        PAMR_CUDA_TRY(cudaLaunchKernelEx(&cfg, propagate_sm100_kernel<R, false>, tmap, tmap1, p));
     } else {
-        propagate_sm100_kernel<R><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, p);
+#ifdef PAMR_FUSED_ITERATIONS
+        if (fused != nullptr) propagate_sm100_kernel<R, true><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, tmap1, p);
+        else
+#else
+        if (fused != nullptr) return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: built without PAMR_FUSED_ITERATIONS");
+#endif
+        propagate_sm100_kernel<R, false><<<grid, NTHREADS, C_::SMEM_BYTES, s>>>(tmap, tmap1, p);
     }
     count_launch();
     PAMR_CUDA_TRY(cudaGetLastError());
@@ -1459,9 +1657,41 @@ int launch_propagate_tuned(const float* aff_tiled, const AffTiling& tiling, cons
         return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: source / affinity base not 16-byte aligned");
     const int sp = pair_pitch(W);
     if (tiling.R == 8)
-        return launch_one<8>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, cls_max, sm_count, dev, dependent, s);
+        return launch_one<8>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, cls_max, sm_count, dev, dependent, nullptr, s);
     if (tiling.R == 10)
-        return launch_one<10>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, cls_max, sm_count, dev, dependent, s);
+        return launch_one<10>(aff_tiled, tiling, src, sp, dst, dst_pitch, dst_pair, B, C, H, W, cls_max, sm_count, dev, dependent, nullptr, s);
+    return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: unsupported tiling R=%d", tiling.R);
+}
+
+// All `iters` (>= 2) propagation steps in ONE launch of the tile kernel: iteration it reads buf[it & 1] and writes
+// buf[(it + 1) & 1] (both in the padded row-pair layout; the input is in buf0), the last one writes `out` ([B,C,H,W]).
+// Tiles of iteration it + 1 start as soon as the tiles around them have finished iteration it (epochs in global
+// memory), so the launch has one cold start and one tail instead of `iters` of each.  Applies when the row strip, if
+// any, fits the kernel's tail (tuned_fusable); `epochs` are tuned_fused_epoch_ints() zeroed ints.
+bool tuned_fusable(const AffTiling& tiling, int B, int C, int H, int W, int dev) {
+    int sm_count = 0;
+    if (device_sm_count(dev, &sm_count) != PAMR_OK || tiling.R == 0) return false;
+    const long long ntiles = (long long)tiling.tiles_x * tiling.tiles_y * B;
+    if (ntiles > 0x7fffffffLL) return false;
+    const int grid = ntiles < sm_count ? (int)ntiles : sm_count;
+    const long long row_items = (long long)B * C * (H - tiling.Ht) * ((W + 31) / 32);
+    if (row_items > 0x7fffffffLL) return false;
+    return tiling.Ht == H || row_strip_in_tail(row_items, ntiles, grid);
+}
+size_t tuned_fused_epoch_ints(const AffTiling& tiling, int B) { return (size_t)tiling.tiles_x * tiling.tiles_y * B + (size_t)B; }
+int launch_propagate_tuned_fused(const float* aff_tiled, const AffTiling& tiling, const float* buf0, const float* buf1, float* out,
+                                 int B, int C, int H, int W, int iters, unsigned* cls_max, int* epochs, int dev, cudaStream_t s) {
+    int sm_count = 0;
+    int rc = device_sm_count(dev, &sm_count);
+    if (rc != PAMR_OK) return rc;
+    if (((uintptr_t)buf0 & 15) != 0 || ((uintptr_t)buf1 & 15) != 0 || ((uintptr_t)aff_tiled & 15) != 0)
+        return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: buffer / affinity base not 16-byte aligned");
+    const int sp = pair_pitch(W);
+    const FusedArgs fa{iters, buf0, buf1, epochs};
+    if (tiling.R == 8)
+        return launch_one<8>(aff_tiled, tiling, nullptr, sp, out, W, false, B, C, H, W, cls_max, sm_count, dev, false, &fa, s);
+    if (tiling.R == 10)
+        return launch_one<10>(aff_tiled, tiling, nullptr, sp, out, W, false, B, C, H, W, cls_max, sm_count, dev, false, &fa, s);
     return set_error(PAMR_ERR_INVALID_ARGUMENT, "tuned propagate: unsupported tiling R=%d", tiling.R);
 }
 

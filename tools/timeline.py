@@ -15,8 +15,8 @@ buf = torch.zeros((5, 4096, 2), dtype=torch.int64, device=dev)
 raw = ctypes.CDLL(wseg_b200._lib.LIB_PATH)
 raw.pamr_debug_set_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
 torch.cuda.synchronize()
-raw.pamr_debug_set_timeline(buf.data_ptr(), CTA, 1)   # record the 2nd of 3 iterations (row-pair in, row-pair out)
-wseg_b200.propagate(aff, mask, D6, 3)
+raw.pamr_debug_set_timeline(buf.data_ptr(), CTA, int(os.environ.get("PROF_SKIP", 1)))   # record the 2nd of 3 iterations (row-pair in, row-pair out); fused launch: PROF_SKIP=0
+wseg_b200.propagate(aff, mask, D6, int(os.environ.get("PROF_ITERS", 3)))
 torch.cuda.synchronize()
 ev = buf.cpu().numpy()
 t0 = min(int(ev[g, 0, 0]) for g in range(3) if ev[g, 0, 0] > 0)

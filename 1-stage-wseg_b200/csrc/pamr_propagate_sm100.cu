@@ -1348,6 +1348,9 @@ propagate_sm100_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
                 pend_tile = tile;
                 pend_it = it;
                 pend_slot = gt & 3;
+                // (with a single tile per iteration the next visit is the same tile one iteration later, which waits for
+                // neighbours that wait for this very announcement: no deferral then)
+                if (vis.mt < 2) announce();
             }
             if (!fused && ti == vis.mt - 1 && prm.tail_cta0 >= 0 && (int)blockIdx.x >= prm.tail_cta0) {
                 const int nw = ((int)gridDim.x - prm.tail_cta0) * NWC;

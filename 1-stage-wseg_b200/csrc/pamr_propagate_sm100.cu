@@ -33,7 +33,11 @@
 //  * remainders (W = H = 321 -> one column, one row): a column strip of at most 2 columns is computed by the
 //    tiles on the right image border from the window they hold anyway (one pixel per lane after every class
 //    pass, weights of the tile's strip pixels in shared memory); a row strip of at most 8 rows is computed by
-//    the CTAs that are idle in the kernel's last wave (or a small launch when there are none).
+//    the CTAs that are idle in the kernel's last wave (or a small launch when there are none);
+//  * iterations are separate launches chained with programmatic dependent launch.  The kernel is written over
+//    "tile visits" (struct Visit) so that the same code also runs ALL iterations in one launch with per-tile
+//    epochs instead of kernel boundaries (template parameter FUSED, -DPAMR_FUSED_ITERATIONS): that variant is
+//    bit-identical and slower, so the product does not instantiate it.
 #include <cuda.h>
 
 #include <atomic>

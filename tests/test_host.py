@@ -231,3 +231,24 @@ def test_header_is_plain_c_and_links(tmp_path):
     torch / Python involved (examples/c_abi_demo.c); running it needs a GPU (tests/test_gpu_parity.py)."""
     _lib.build()
     assert os.path.exists(_build_c_demo(tmp_path))
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU leg the driver runs beside the GPU arm) prints one JSON line with the
+    contract's keys, honours --steps / --warmup as given and scales its sample with --gpus."""
+    import json
+    import subprocess
+    import sys
+    for gpus in (1, 2):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", str(gpus),
+                            "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-2000:]
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["metric"].startswith("PAMR Mpix/s") and d["unit"] == "Mpix/s"
+        assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == gpus and d["higher_is_better"] is True
+        assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+        assert d["config"]["sample_batch"] == gpus and "B=%d per step" % gpus in d["config"]["workload"]
+        assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert d["gpu_launches"] == 0

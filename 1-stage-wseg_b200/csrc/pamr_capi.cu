@@ -187,7 +187,7 @@ struct ForwardPlan {
 ForwardPlan plan_forward(int B, int K, int C, int H, int W, int h, int w, const Dilations& dil, int iters) {
     ForwardPlan p;
     const size_t HW = (size_t)H * W;
-    p.tiling = tuned_tiling(B, H, W, dil);
+    p.tiling = tuned_tiling(B, C, H, W, dil);
     const size_t aff_floats = p.tiling.R > 0 ? p.tiling.floats : (size_t)B * 8 * dil.nd * HW;
     p.aff_bytes = align_up(sizeof(float) * aff_floats, 256);
     p.scratch_bytes = align_up(propagate_scratch_bytes(B, C, H, W, dil, iters, p.tiling.R > 0), 256);
@@ -334,7 +334,7 @@ int pamr_pseudo_labels_host_f32(const float* h_img, const float* h_mask, const f
     const size_t HW = (size_t)H * W, hw = (size_t)h * w;
     const size_t n_img = sizeof(float) * (size_t)B * K * HW, n_ims = sizeof(float) * (size_t)B * K * hw;
     const size_t n_mask = sizeof(float) * (size_t)B * C * hw, n_lab = sizeof(float) * (size_t)B * (C - 1);
-    const AffTiling tiling = tuned_tiling(B, h, w, dil);
+    const AffTiling tiling = tuned_tiling(B, C, h, w, dil);
     const size_t n_aff = sizeof(float) * (tiling.R > 0 ? tiling.floats : (size_t)B * 8 * nd * hw);
     const size_t n_out = (size_t)B * HW;
     const size_t n_max = sizeof(unsigned) * (size_t)B * C;

@@ -216,7 +216,7 @@ size_t affinity_pitched_image_bytes(int B, int K, int H, int W);
 int launch_aff_relayout(const float* aff_std, float* aff_tiled, int B, int H, int W, const AffTiling& tiling,
                         cudaStream_t s);
 // Tiling of the tuned propagation kernel for this problem; R == 0 when only the generic kernel applies.
-AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil);
+AffTiling tuned_tiling(int B, int C, int H, int W, const Dilations& dil);
 size_t propagate_scratch_bytes(int B, int C, int H, int W, const Dilations& dil, int iters, bool aff_is_tiled);
 int launch_propagate(const float* aff, bool aff_is_tiled, const float* m_in, float* m_out, void* scratch,
                      size_t scratch_bytes, int B, int C, int H, int W, const Dilations& dil, int iters,

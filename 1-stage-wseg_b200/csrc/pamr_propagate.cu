@@ -113,7 +113,7 @@ struct ScratchPlan {
 ScratchPlan plan_scratch(int B, int C, int H, int W, const Dilations& dil, int iters, bool aff_is_tiled) {
     ScratchPlan p{0, 0, 0, 0};
     if (iters <= 0) return p;
-    const AffTiling t = tuned_tiling(B, H, W, dil);
+    const AffTiling t = tuned_tiling(B, C, H, W, dil);
     if (t.R > 0) {
         // tuned kernel: two ping-pong buffers in the row-pair layout [B*C][ceil(H/2)][Wp][2], Wp a multiple of 16
         // (TMA reads 64-bit elements and needs 16-byte global strides; whole 128-byte lines per row pair)
@@ -204,7 +204,7 @@ int launch_affinity_propagate(const float* img, int K, float* aff_out, float* im
     // small maps with the affinity computed here: one launch does everything (the affinity stays in registers)
     if (img != nullptr && iters >= 1 && resident_plan(B, C, H, W, dil, iters, dev).ok)
         return launch_resident(img, K, m_in, m_out, scratch, scratch_bytes, B, C, H, W, dil, iters, cls_max, dev, s);
-    const AffTiling tiling = tuned_tiling(B, H, W, dil);
+    const AffTiling tiling = tuned_tiling(B, C, H, W, dil);
     const bool tuned = tiling.R > 0;
     if (cls_max != nullptr) {
         // zeroed by a kernel, not cudaMemsetAsync: a memset node in front of the fork/join events below

@@ -1590,8 +1590,8 @@ extern "C" void pamr_debug_set_timeline(long long* dev_buf, int cta, int skip) {
 // launch ~ 8 + 1.3 us per 1000 items -- and the cheapest wins.  E.g. 321 x 321, B=16: R=10, 10 x 8 tiles, column
 // 320 by the border tiles, row 320 in the tail of the same launch.  All paths add the 48 products of a pixel in
 // the same order, so the result does not depend on the tiling (nor, therefore, on how a batch is sharded).  The
-// model prices the reference's 21 classes; the SM count is the current device's.
-AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
+// row-strip placement is priced for the caller's class count; the SM count is the current device's.
+AffTiling tuned_tiling(int B, int C, int H, int W, const Dilations& dil) {
     static const int want[6] = {1, 2, 4, 8, 12, 24};
     AffTiling t{};
     if (dil.nd != 6 || W < TX || H < 8) return t;
@@ -1599,7 +1599,6 @@ AffTiling tuned_tiling(int B, int H, int W, const Dilations& dil) {
         if (dil.d[i] != want[i]) return t;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess || device_sm_count(dev, &sms) != PAMR_OK || sms <= 0) sms = 148;
-    const int C = 21;
     double best_cost = 1e30;
     for (int r = 8; r <= 10; r += 2) {
         const int ty = NW * r;

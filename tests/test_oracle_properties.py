@@ -14,7 +14,7 @@ def _mask(rng, B, C, H, W):
     return e / e.sum(1, keepdims=True)
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(dims, st.integers(0, 10_000))
 def test_pamr_is_a_convex_combination(d, seed):
     B, C, H, W = d
@@ -28,7 +28,7 @@ def test_pamr_is_a_convex_combination(d, seed):
     assert np.abs(aff.sum(1) - 1).max() <= 1e-5 and (aff >= 0).all()
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(dims, st.integers(0, 10_000))
 def test_pamr_is_linear_in_the_mask_and_shift_invariant_in_the_image(d, seed):
     B, C, H, W = d
@@ -40,7 +40,7 @@ def test_pamr_is_linear_in_the_mask_and_shift_invariant_in_the_image(d, seed):
     assert np.abs(oracle.affinity(image, D6) - oracle.affinity(image + np.float32(0.5), D6)).max() <= 5e-6
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(dims, st.integers(0, 10_000))
 def test_pseudo_labels_are_consistent_with_pseudo_gt(d, seed):
     B, C, H, W = d
@@ -53,7 +53,7 @@ def test_pseudo_labels_are_consistent_with_pseudo_gt(d, seed):
     assert (np.argmax(pg, 1)[has] == lab[has]).all()
 
 
-@settings(max_examples=20, deadline=None)
+@settings(max_examples=20, deadline=None, derandomize=True)
 @given(st.tuples(st.integers(1, 3), st.integers(2, 6), st.integers(1, 9), st.integers(1, 9), st.integers(1, 20), st.integers(1, 20)),
        st.integers(0, 10_000))
 def test_mask_ce_gradient_sums_to_zero_over_classes_and_vanishes_where_ignored(d, seed):
@@ -67,12 +67,13 @@ def test_mask_ce_gradient_sums_to_zero_over_classes_and_vanishes_where_ignored(d
     gl = (pg.reshape(B, C, -1).sum(-1)[:, 1:] > 0).astype(np.float32)
     loss, grad = oracle.balanced_mask_loss_ce(logits, pg, gl, np.ones(B, np.float32))
     assert (loss >= 0).all() and np.isfinite(grad).all()
-    assert np.abs(grad.sum(1)).max() <= 1e-8
+    # each fp32 gradient carries its own rounding (half an ulp of its magnitude): the class sum is zero to a few ulps of the largest entry
+    assert np.abs(grad.sum(1)).max() <= 1e-6 * max(float(np.abs(grad).max()), 1e-30)
     empty = pg.reshape(B, -1).sum(-1) == 0
     assert not grad[empty].any() and not loss[empty].any()
 
 
-@settings(max_examples=20, deadline=None)
+@settings(max_examples=20, deadline=None, derandomize=True)
 @given(st.integers(1, 6), st.integers(2, 5), st.integers(2, 16), st.integers(2, 16), st.integers(0, 10_000))
 def test_merge_of_identical_unpadded_scales_is_the_identity(S, C, H, W, seed):
     m = _mask(np.random.RandomState(seed), 1, C, H, W)[0]

@@ -26,12 +26,11 @@ resize_kernel(const float* __restrict__ src, float* __restrict__ dst, int h, int
     dst[(n * H + y) * W + x] = bilerp(src + n * h * w, w, ly, lx);
 }
 
-// v = gate * bilinear(m); optional store; block max -> atomicMax(cls_max[b,c]).
+// v = gate * m; optional store; block max -> atomicMax(cls_max[b,c]).  Source and target have the same size.
 // grid: (tiles_x, tiles_y, B*C)
-template <bool kResize>
 __global__ void __launch_bounds__(EP_BX * EP_BY)
 clean_kernel(const float* __restrict__ m, const float* __restrict__ labels, float* __restrict__ cleaned,
-             unsigned* __restrict__ cls_max, int C, int h, int w, int H, int W, float sh, float sw) {
+             unsigned* __restrict__ cls_max, int C, int H, int W) {
     const int x = blockIdx.x * EP_BX + threadIdx.x;
     const int y = blockIdx.y * EP_BY + threadIdx.y;
     const size_t plane = blockIdx.z;
@@ -39,12 +38,7 @@ clean_kernel(const float* __restrict__ m, const float* __restrict__ labels, floa
     const bool valid = (x < W) && (y < H);
     float v = 0.f;
     if (valid) {
-        if (kResize) {
-            const Lerp ly = make_lerp(y, sh, h), lx = make_lerp(x, sw, w);
-            v = bilerp(m + plane * h * w, w, ly, lx);
-        } else {
-            v = __ldg(m + (plane * H + y) * W + x);
-        }
+        v = __ldg(m + (plane * H + y) * W + x);
         if (labels != nullptr && c > 0) v = __fmul_rn(v, __ldg(labels + (size_t)b * (C - 1) + (c - 1)));
         if (cleaned != nullptr) cleaned[(plane * H + y) * W + x] = v;
     }
@@ -58,6 +52,87 @@ clean_kernel(const float* __restrict__ m, const float* __restrict__ labels, floa
             u = red[threadIdx.x];
             u = __reduce_max_sync((1u << EP_BY) - 1u, u);
             if (threadIdx.x == 0 && u != 0u) atomicMax(cls_max + plane, u);
+        }
+    }
+}
+
+// ---- the resized epilogue (stage_net's real call shapes: masks 81x81 / 41x41 -> 321x321, SoftMaxAE.py:266) ----
+// Column walk: a thread owns one output column x of a band of output rows.  bilerp() is
+//     v = ly.l0 * t0 + ly.l1 * t1,   t0 = lx.l0 * p[i0][x0] + lx.l1 * p[i0][x1],   t1 = the same on row i1,
+// and t0 / t1 depend on the SOURCE row only: when the map is enlarged k times a thread recomputes them every k-th
+// output row (the new t0 usually is the old t1), and an output pixel costs 3 floating-point instructions instead
+// of 4 loads + 9.  Every value is produced by the same expression in the same order as bilerp(), so the results are
+// bit-identical to the one-thread-per-pixel kernels this replaces (0.273 -> see profiles/r02_real_shape_times.txt).
+struct RowPair {
+    int i0, i1;  // source rows currently held in t0 / t1
+};
+__device__ __forceinline__ float lerp_row(const float* __restrict__ pl, int off, const Lerp& lx) {
+    return __fadd_rn(__fmul_rn(lx.l0, __ldg(pl + off + lx.i0)), __fmul_rn(lx.l1, __ldg(pl + off + lx.i1)));
+}
+
+constexpr int CW_THREADS = 256;
+constexpr int CW_ROWS = 32;      // output rows per band in the max / store pass
+constexpr int CW_TAB = 512;      // row table: the Lerp of every output row a block touches, computed once per block
+constexpr int PW_THREADS = 128;  // label pass: 21 classes per thread (t0 / t1 of every class in registers), 4 blocks per SM
+constexpr int PW_CB = 21;        // classes held per thread in the label pass (the reference's 21; more go to the per-pixel kernel)
+
+// grid: (ceil(nbands * W / CW_THREADS), planes); thread t of a plane: band = t / W, x = t % W.
+// labels == nullptr: plain resize (C is then irrelevant); cleaned / cls_max optional.  h * w < 2^31.
+__global__ void __launch_bounds__(CW_THREADS)
+clean_walk_kernel(const float* __restrict__ m, const float* __restrict__ labels, float* __restrict__ cleaned,
+                  unsigned* __restrict__ cls_max, int C, int h, int w, int H, int W, float sh, float sw, int nbands) {
+    __shared__ float4 tab[CW_TAB];  // (i0, i1, l0, l1) of output row row_lo + k: the same for every thread of a band
+    __shared__ unsigned red[CW_THREADS / 32];
+    const size_t plane = blockIdx.y;
+    const int t_lo = blockIdx.x * CW_THREADS, t = t_lo + threadIdx.x;
+    const int row_lo = (t_lo / W) * CW_ROWS;
+    const int row_hi = min(H, (min(t_lo + CW_THREADS - 1, nbands * W - 1) / W + 1) * CW_ROWS);
+    const bool use_tab = row_hi - row_lo <= CW_TAB;  // narrow maps (a block spans many bands): rows computed in place
+    if (use_tab) {
+        for (int k = threadIdx.x; k < row_hi - row_lo; k += CW_THREADS) {
+            const Lerp ly = make_lerp(row_lo + k, sh, h);
+            tab[k] = make_float4(__int_as_float(ly.i0), __int_as_float(ly.i1), ly.l0, ly.l1);
+        }
+        __syncthreads();
+    }
+    unsigned best = 0u;
+    if (t < nbands * W) {
+        const int band = t / W, x = t - band * W;
+        const int y1 = min(H, (band + 1) * CW_ROWS);
+        const bool gated = labels != nullptr && (plane % C) > 0;
+        const float g = gated ? __ldg(labels + (plane / C) * (size_t)(C - 1) + (plane % C - 1)) : 1.f;
+        const float* __restrict__ pl = m + plane * h * w;
+        float* __restrict__ dst = cleaned != nullptr ? cleaned + plane * H * W + x : nullptr;
+        const Lerp lx = make_lerp(x, sw, w);
+        RowPair cur{-1, -1};
+        float t0 = 0.f, t1 = 0.f;
+        for (int y = band * CW_ROWS; y < y1; ++y) {
+            Lerp ly;
+            if (use_tab) {
+                const float4 e = tab[y - row_lo];
+                ly.i0 = __float_as_int(e.x); ly.i1 = __float_as_int(e.y); ly.l0 = e.z; ly.l1 = e.w;
+            } else {
+                ly = make_lerp(y, sh, h);
+            }
+            if (ly.i0 != cur.i0 || ly.i1 != cur.i1) {
+                t0 = (ly.i0 == cur.i1) ? t1 : lerp_row(pl, ly.i0 * w, lx);
+                t1 = (ly.i1 == ly.i0) ? t0 : lerp_row(pl, ly.i1 * w, lx);
+                cur.i0 = ly.i0;
+                cur.i1 = ly.i1;
+            }
+            float v = __fadd_rn(__fmul_rn(ly.l0, t0), __fmul_rn(ly.l1, t1));
+            if (gated) v = __fmul_rn(v, g);
+            if (dst != nullptr) dst[(size_t)y * W] = v;
+            best = max(best, ordered_from_float(v));
+        }
+    }
+    if (cls_max != nullptr) {
+        best = __reduce_max_sync(0xffffffffu, best);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x < CW_THREADS / 32) {
+            best = __reduce_max_sync((1u << (CW_THREADS / 32)) - 1u, red[threadIdx.x]);
+            if (threadIdx.x == 0 && best != 0u) atomicMax(cls_max + plane, best);
         }
     }
 }
@@ -131,6 +206,101 @@ pseudo_labels_kernel(const float* __restrict__ m, const float* __restrict__ labe
         __syncthreads();
         for (int c = threadIdx.x; c < C; c += PL_THREADS)
             if (cnt[c] != 0) atomicAdd(class_count + (size_t)b * C + c, cnt[c]);
+    }
+}
+
+// The label pass of the resized epilogue as a column walk (see clean_walk_kernel): a thread keeps t0 / t1 of all
+// C <= PW_CB classes in registers and walks `rows` output rows (chosen by the launcher so that the last wave of
+// blocks is full).  Everything over the classes is branch-free (classes beyond C re-read class C-1 and carry an
+// infinite threshold), so that the 2 x 21 loads of a new source row are all in flight before the first is used.
+// grid: (ceil(nbands * W / PW_THREADS), B); C * h * w < 2^31.
+__device__ __forceinline__ void lerp_row_all(const float* __restrict__ pimg, int C, int hw, int off, const Lerp& lx,
+                                             float (&tt)[PW_CB]) {
+    float a[PW_CB], c[PW_CB];
+#pragma unroll
+    for (int j = 0; j < PW_CB; ++j) {
+        const int o = min(j, C - 1) * hw + off;
+        a[j] = __ldg(pimg + o + lx.i0);
+        c[j] = __ldg(pimg + o + lx.i1);
+    }
+#pragma unroll
+    for (int j = 0; j < PW_CB; ++j) tt[j] = __fadd_rn(__fmul_rn(lx.l0, a[j]), __fmul_rn(lx.l1, c[j]));
+}
+
+__global__ void __launch_bounds__(PW_THREADS, 4)
+pseudo_labels_walk_kernel(const float* __restrict__ m, const float* __restrict__ labels,
+                          const unsigned* __restrict__ cls_max, uint8_t* __restrict__ label,
+                          float* __restrict__ pseudo_gt, int* __restrict__ class_count, int C, int h, int w, int H,
+                          int W, float sh, float sw, float bg_cut, float fg_cut, float low_cut, bool max_is_gated,
+                          int rows, int nbands) {
+    __shared__ float2 thr_gate[PW_CB];  // (threshold, label gate) per class
+    __shared__ int cnt[PW_CB];
+    const int b = blockIdx.y;
+    if (threadIdx.x < PW_CB) {
+        const int c = threadIdx.x;
+        float g = 1.f, th = __int_as_float(0x7f800000);  // classes beyond C: never selected
+        if (c < C) {  // thresholds exactly as in pseudo_labels_kernel
+            g = (labels != nullptr && c > 0) ? __ldg(labels + (size_t)b * (C - 1) + (c - 1)) : 1.f;
+            float mx = float_from_ordered(__ldg(cls_max + (size_t)b * C + c));
+            if (!max_is_gated) mx = __fmul_rn(mx, g);
+            th = fmaxf(__fmul_rn(mx, c == 0 ? bg_cut : fg_cut), low_cut);
+        }
+        thr_gate[c] = make_float2(th, g);
+        cnt[c] = 0;
+    }
+    __syncthreads();
+    const size_t HW = (size_t)H * W;
+    const int hw = h * w;
+    const int t = blockIdx.x * PW_THREADS + threadIdx.x;
+    if (t < nbands * W) {
+        const int band = t / W, x = t - band * W;
+        const int y1 = min(H, (band + 1) * rows);
+        const float* __restrict__ pimg = m + (size_t)b * C * hw;
+        const Lerp lx = make_lerp(x, sw, w);
+        RowPair cur{-1, -1};
+        float t0[PW_CB], t1[PW_CB];
+#pragma unroll
+        for (int j = 0; j < PW_CB; ++j) t0[j] = t1[j] = 0.f;
+        for (int y = band * rows; y < y1; ++y) {
+            const Lerp ly = make_lerp(y, sh, h);
+            if (ly.i0 != cur.i0 || ly.i1 != cur.i1) {
+                if (ly.i0 == cur.i1) {
+#pragma unroll
+                    for (int j = 0; j < PW_CB; ++j) t0[j] = t1[j];
+                } else {
+                    lerp_row_all(pimg, C, hw, ly.i0 * w, lx, t0);
+                }
+                if (ly.i1 == ly.i0) {
+#pragma unroll
+                    for (int j = 0; j < PW_CB; ++j) t1[j] = t0[j];
+                } else {
+                    lerp_row_all(pimg, C, hw, ly.i1 * w, lx, t1);
+                }
+                cur.i0 = ly.i0;
+                cur.i1 = ly.i1;
+            }
+            // x -> fl(x * 1) is the identity, so the un-gated classes (class 0, or no labels at all: gate 1) go
+            // through the same multiply as the gated ones
+            unsigned hits = 0u;
+#pragma unroll
+            for (int j = 0; j < PW_CB; ++j) {
+                const float2 tg = thr_gate[j];
+                const float v = __fadd_rn(__fmul_rn(ly.l0, t0[j]), __fmul_rn(ly.l1, t1[j]));
+                if (__fmul_rn(v, tg.y) > tg.x) hits |= 1u << j;
+            }
+            const bool one = __popc(hits) == 1;
+            const int first = __ffs(hits) - 1;
+            const size_t i = (size_t)y * W + x;
+            if (label != nullptr) label[(size_t)b * HW + i] = one ? (uint8_t)first : (uint8_t)255;
+            if (pseudo_gt != nullptr)
+                for (int c = 0; c < C; ++c) pseudo_gt[((size_t)b * C + c) * HW + i] = (one && c == first) ? 1.f : 0.f;
+            if (class_count != nullptr && one) atomicAdd(&cnt[first], 1);
+        }
+    }
+    if (class_count != nullptr) {
+        __syncthreads();
+        if (threadIdx.x < C && threadIdx.x < PW_CB && cnt[threadIdx.x] != 0)
+            atomicAdd(class_count + (size_t)b * C + threadIdx.x, cnt[threadIdx.x]);
     }
 }
 
@@ -222,12 +392,20 @@ int launch_resize_bilinear(const float* src, float* dst, int n_planes, int h, in
         return PAMR_OK;
     }
     dim3 block(EP_BX, EP_BY);
+    const int nbands = (H + CW_ROWS - 1) / CW_ROWS;
+    const bool walk = H >= 2 * h && (long long)nbands * W < (1ll << 30) && (long long)h * w < (1ll << 31);  // enlarging: source rows are re-used
     for (int n0 = 0; n0 < n_planes; n0 += 65535) {
         const int nn = min(65535, n_planes - n0);
-        dim3 grid((W + EP_BX - 1) / EP_BX, (H + EP_BY - 1) / EP_BY, nn);
-        if (grid.y > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "resize: H too large");
-        resize_kernel<<<grid, block, 0, s>>>(src + (size_t)n0 * h * w, dst + (size_t)n0 * H * W, h, w, H, W,
-                                             scale_of(h, H), scale_of(w, W));
+        if (walk) {
+            dim3 grid((unsigned)((nbands * W + CW_THREADS - 1) / CW_THREADS), nn);
+            clean_walk_kernel<<<grid, CW_THREADS, 0, s>>>(src + (size_t)n0 * h * w, nullptr, dst + (size_t)n0 * H * W, nullptr,
+                                                          1, h, w, H, W, scale_of(h, H), scale_of(w, W), nbands);
+        } else {
+            dim3 grid((W + EP_BX - 1) / EP_BX, (H + EP_BY - 1) / EP_BY, nn);
+            if (grid.y > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "resize: H too large");
+            resize_kernel<<<grid, block, 0, s>>>(src + (size_t)n0 * h * w, dst + (size_t)n0 * H * W, h, w, H, W,
+                                                 scale_of(h, H), scale_of(w, W));
+        }
         count_launch();
     }
     PAMR_CUDA_TRY(cudaGetLastError());
@@ -239,14 +417,19 @@ int launch_clean(const float* m, const float* labels, float* cleaned, unsigned* 
     if (cls_max != nullptr) PAMR_CUDA_TRY(cudaMemsetAsync(cls_max, 0, sizeof(unsigned) * (size_t)B * C, s));
     if (cleaned == nullptr && cls_max == nullptr) return PAMR_OK;
     if ((size_t)B * C > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "clean: B*C must be <= 65535");
-    dim3 block(EP_BX, EP_BY);
-    dim3 grid((W + EP_BX - 1) / EP_BX, (H + EP_BY - 1) / EP_BY, B * C);
-    if (grid.y > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "clean: H too large");
-    if (h == H && w == W)
-        clean_kernel<false><<<grid, block, 0, s>>>(m, labels, cleaned, cls_max, C, h, w, H, W, 0.f, 0.f);
-    else
-        clean_kernel<true><<<grid, block, 0, s>>>(m, labels, cleaned, cls_max, C, h, w, H, W, scale_of(h, H),
-                                                  scale_of(w, W));
+    if (h == H && w == W) {
+        dim3 block(EP_BX, EP_BY);
+        dim3 grid((W + EP_BX - 1) / EP_BX, (H + EP_BY - 1) / EP_BY, B * C);
+        if (grid.y > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "clean: H too large");
+        clean_kernel<<<grid, block, 0, s>>>(m, labels, cleaned, cls_max, C, H, W);
+    } else {
+        const int nbands = (H + CW_ROWS - 1) / CW_ROWS;
+        if ((long long)nbands * W >= (1ll << 30) || (long long)h * w >= (1ll << 31))
+            return set_error(PAMR_ERR_INVALID_ARGUMENT, "clean: map too large");
+        dim3 grid((unsigned)((nbands * W + CW_THREADS - 1) / CW_THREADS), B * C);
+        clean_walk_kernel<<<grid, CW_THREADS, 0, s>>>(m, labels, cleaned, cls_max, C, h, w, H, W, scale_of(h, H),
+                                                      scale_of(w, W), nbands);
+    }
     count_launch();
     PAMR_CUDA_TRY(cudaGetLastError());
     return PAMR_OK;
@@ -269,7 +452,24 @@ int launch_pseudo_labels(const float* m, const float* labels, const unsigned* cl
         pseudo_labels_kernel<false, 7><<<grid, PL_THREADS, smem, s>>>(m, labels, cls_max, label, pseudo_gt, class_count,
                                                                       C, h, w, H, W, 0.f, 0.f, bg_cut, fg_cut, low_cut,
                                                                       max_is_gated);
-    else
+    else if (C <= PW_CB && (long long)((H + 7) / 8) * W < (1ll << 30) && (long long)C * h * w < (1ll << 31)) {
+        // rows per band: the candidate with the cheapest schedule, waves of 4 blocks per SM x (rows + the loads of a
+        // band's first row pair, worth about 3 rows)
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) != cudaSuccess || device_sm_count(dev, &sms) != PAMR_OK || sms <= 0) sms = 148;
+        int rows = 8;
+        long long best_cost = -1;
+        for (int r = 8; r <= 32; ++r) {
+            const long long blocks = ((long long)((H + r - 1) / r) * W + PW_THREADS - 1) / PW_THREADS * B;
+            const long long cost = ((blocks + 4ll * sms - 1) / (4ll * sms)) * (r + 3);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; rows = r; }
+        }
+        const int nbands = (H + rows - 1) / rows;
+        dim3 wgrid((unsigned)((nbands * W + PW_THREADS - 1) / PW_THREADS), B);
+        pseudo_labels_walk_kernel<<<wgrid, PW_THREADS, 0, s>>>(m, labels, cls_max, label, pseudo_gt, class_count, C, h, w,
+                                                               H, W, scale_of(h, H), scale_of(w, W), bg_cut, fg_cut,
+                                                               low_cut, max_is_gated, rows, nbands);
+    } else
         pseudo_labels_kernel<true, 7><<<grid, PL_THREADS, smem, s>>>(m, labels, cls_max, label, pseudo_gt, class_count,
                                                                   C, h, w, H, W, scale_of(h, H), scale_of(w, W),
                                                                   bg_cut, fg_cut, low_cut, max_is_gated);

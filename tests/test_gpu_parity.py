@@ -516,3 +516,42 @@ def test_random_shapes_vs_oracle():
         mask = e / e.sum(1, keepdims=True)
         out = N(wseg_b200.PAMR(it, D6).to(DEV)(G(image), G(mask)))
         assert np.abs(out - oracle.pamr_forward(image, mask, it, D6)).max() <= TOL, (B, C, H, W, it)
+
+
+# ---------------------------------------------------------------- resized epilogue (column-walk kernels), bit-exact vs oracle
+
+@pytest.mark.parametrize("shape", [
+    (2, 21, 81, 81, 321, 321),   # stage_net, stride-4 masks
+    (3, 21, 41, 41, 321, 321),   # stride-8 masks
+    (2, 5, 20, 30, 97, 65),      # non-integer enlargement
+    (1, 21, 33, 47, 40, 50),     # barely enlarged: the source row pair changes on almost every row
+    (2, 21, 64, 64, 32, 32),     # reduction: every output row has a new source row pair
+    (1, 22, 16, 16, 64, 64),     # more than 21 classes: the one-thread-per-pixel label kernel
+    (2, 1, 9, 9, 40, 40),        # a single class (no gated class at all)
+    (1, 21, 1, 1, 17, 13),       # 1x1 source
+    (2, 4, 10, 3, 300, 5),       # narrow map: a block of the store pass spans many bands (rows computed in place)
+    (1, 21, 8, 8, 8, 64),        # enlarged in x only
+    (1, 3, 5, 7, 1, 1),          # 1x1 target (scale 0)
+])
+def test_resized_epilogue_bit_exact_vs_oracle(shape):
+    """_rescale_and_clean -> pseudo_gtmask -> argmax at a target size different from the mask size (SoftMaxAE.py:263-268,
+    29-50, 61-67): cleaned masks, class maxima, labels, one-hot and counts are integer / single-expression work and
+    must be bit-identical to the oracle, with and without label gating."""
+    B, C, h, w, H, W = shape
+    masks = synth.mask_blobs(B, C, h, w, 31) if min(h, w) >= 8 else synth.mask_softmax(B, C, h, w, 31)
+    L = _lib.lib()
+    for labels in ([synth.labels_bernoulli(B, C, 32, p=0.4), None] if C > 1 else [None]):
+        lab_np = labels if labels is not None else np.ones((B, max(C - 1, 0)), np.float32)
+        ref_clean = oracle.rescale_and_clean(masks, (H, W), lab_np) if C > 1 else oracle.resize_bilinear(masks, (H, W))
+        ref_lab, ref_pg = oracle.pseudo_labels(ref_clean), oracle.pseudo_gtmask(ref_clean)
+        lab_t = G(labels) if labels is not None else None
+        cleaned, cmax = wseg_b200.rescale_and_clean(G(masks), (H, W), lab_t, return_class_max=True)
+        np.testing.assert_array_equal(N(cleaned), ref_clean)
+        got_max = np.array([[L.pamr_float_from_ordered(int(v) & 0xffffffff) for v in row] for row in N(cmax)], dtype=np.float32)
+        np.testing.assert_array_equal(got_max, ref_clean.reshape(B, C, -1).max(-1))
+        lab, onehot, counts = wseg_b200.pseudo_labels(G(masks), lab_t, (H, W), return_onehot=True, return_counts=True)
+        np.testing.assert_array_equal(N(lab), ref_lab)
+        np.testing.assert_array_equal(N(onehot), ref_pg)
+        np.testing.assert_array_equal(N(counts), np.stack([(ref_lab == c).reshape(B, -1).sum(1) for c in range(C)], 1))
+        np.testing.assert_array_equal(N(wseg_b200.pseudo_labels(G(masks), lab_t, (H, W))), ref_lab)  # labels only
+        np.testing.assert_array_equal(N(wseg_b200.resize_bilinear(G(masks), (H, W))), oracle.resize_bilinear(masks, (H, W)))

@@ -193,6 +193,137 @@ ce_forward_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ 
     }
 }
 
+// Forward with up-sampled logits (the training shapes: logits 81x81 / 41x41, labels 321x321) as a COLUMN WALK, like
+// the resized epilogue (pamr_epilogue.cu): a thread owns one label column of a band of label rows and keeps, for all
+// C <= CW_CB classes, the x-interpolated logits of the two source rows (t0, t1 of bilerp) in registers; a label row
+// whose source row pair is unchanged costs one FMUL/FMUL/FADD per class instead of four loads and nine operations.
+// Per pixel the values and the log-sum-exp recurrence are those of ce_forward_kernel (same expressions, same batches
+// of CE_BATCH classes), so lse / coef are bit-identical; only the order of the double sum differs.
+// grid (ceil(nbands * W / CW_THREADS), B); C * h * w < 2^31
+constexpr int CW_THREADS = 128;
+constexpr int CW_CB = 21;
+static_assert(CW_CB % CE_BATCH == 0, "whole batches");
+__device__ __forceinline__ void ce_row_all(const float* __restrict__ pimg, int C, int hw, int off, const Lerp& lx,
+                                           float (&tt)[CW_CB]) {
+    float a[CW_CB], c[CW_CB];
+#pragma unroll
+    for (int j = 0; j < CW_CB; ++j) {
+        const int o = min(j, C - 1) * hw + off;
+        a[j] = __ldg(pimg + o + lx.i0);
+        c[j] = __ldg(pimg + o + lx.i1);
+    }
+#pragma unroll
+    for (int j = 0; j < CW_CB; ++j) tt[j] = __fadd_rn(__fmul_rn(lx.l0, a[j]), __fmul_rn(lx.l1, c[j]));
+}
+
+__global__ void __launch_bounds__(CW_THREADS, 4)
+ce_forward_walk_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ label, const int* __restrict__ count,
+                       const float* __restrict__ gt_labels, double* __restrict__ acc, unsigned* __restrict__ ticket,
+                       float* __restrict__ bw_out, float* __restrict__ loss, float* __restrict__ lse_out,
+                       float* __restrict__ coef_out, int C, int h, int w, int H, int W, float sh, float sw, double inv_hw,
+                       int rows, int nbands) {
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const size_t HW = (size_t)H * W;
+    const int hw = h * w;
+    __shared__ float s_cw[CW_CB];
+    __shared__ float s_tot;
+    __shared__ double red[CW_THREADS / 32];
+    if (tid == 0) {  // class weights of this image (SoftMaxAE.py:71-74), as in ce_forward_kernel
+        float tot = 0.f;
+        for (int c = 0; c < C; ++c) tot = __fadd_rn(tot, (float)count[(size_t)b * C + c]);
+        s_tot = tot;
+    }
+    __syncthreads();
+    if (tid < C) s_cw[tid] = __fdiv_rn(__fsub_rn(s_tot, (float)count[(size_t)b * C + tid]), __fadd_rn(1.f, s_tot));
+    __syncthreads();
+    double term = 0.0;
+    const int t = blockIdx.x * CW_THREADS + tid;
+    if (t < nbands * W) {
+        const int band = t / W, x = t - band * W;
+        const int y1 = min(H, (band + 1) * rows);
+        const float* __restrict__ pimg = logits + (size_t)b * C * hw;
+        const Lerp lx = make_lerp(x, sw, w);
+        int ci0 = -1, ci1 = -1;
+        float t0[CW_CB], t1[CW_CB];
+#pragma unroll
+        for (int j = 0; j < CW_CB; ++j) t0[j] = t1[j] = 0.f;
+        for (int y = band * rows; y < y1; ++y) {
+            const Lerp ly = make_lerp(y, sh, h);
+            if (ly.i0 != ci0 || ly.i1 != ci1) {
+                if (ly.i0 == ci1) {
+#pragma unroll
+                    for (int j = 0; j < CW_CB; ++j) t0[j] = t1[j];
+                } else {
+                    ce_row_all(pimg, C, hw, ly.i0 * w, lx, t0);
+                }
+                if (ly.i1 == ly.i0) {
+#pragma unroll
+                    for (int j = 0; j < CW_CB; ++j) t1[j] = t0[j];
+                } else {
+                    ce_row_all(pimg, C, hw, ly.i1 * w, lx, t1);
+                }
+                ci0 = ly.i0;
+                ci1 = ly.i1;
+            }
+            const size_t p = (size_t)b * HW + (size_t)y * W + x;
+            const int lab = label[p];
+            float lse = 0.f, coef = 0.f;
+            if (lab < C) {
+                float m = -INFINITY, s = 0.f, zl = 0.f;
+#pragma unroll
+                for (int c0 = 0; c0 < CW_CB; c0 += CE_BATCH) {
+                    float vb[CE_BATCH];
+#pragma unroll
+                    for (int j = 0; j < CE_BATCH; ++j) {  // classes beyond C: -inf, which leaves the maximum and the sum alone
+                        const float z = __fadd_rn(__fmul_rn(ly.l0, t0[c0 + j]), __fmul_rn(ly.l1, t1[c0 + j]));
+                        vb[j] = (c0 + j < C) ? z : -INFINITY;
+                    }
+                    float bm = vb[0];
+#pragma unroll
+                    for (int j = 1; j < CE_BATCH; ++j) bm = fmaxf(bm, vb[j]);
+                    if (bm > m) {  // one rescale per batch
+                        s *= ce_ex2((m - bm) * CE_LOG2E);
+                        m = bm;
+                    }
+#pragma unroll
+                    for (int j = 0; j < CE_BATCH; ++j) {
+                        if (c0 + j == lab) zl = vb[j];
+                        s += ce_ex2((vb[j] - m) * CE_LOG2E);
+                    }
+                }
+                lse = m + logf(s);
+                const float cw = s_cw[lab];
+                term += (double)cw * (double)(lse - zl);
+                coef = cw / (float)HW;
+            }
+            lse_out[p] = lse;
+            coef_out[p] = coef;
+        }
+    }
+    // block sum in double -> one atomic per block; the image's last block finishes the loss
+    for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+    if ((tid & 31) == 0) red[tid >> 5] = term;
+    __syncthreads();
+    if (tid == 0) {
+        double tsum = 0.0;
+        for (int k = 0; k < CW_THREADS / 32; ++k) tsum += red[k];
+        if (tsum != 0.0) atomicAdd(acc + b, tsum);
+        __threadfence();
+        const unsigned done = atomicAdd(ticket + b, 1u) + 1u;
+        if (done == gridDim.x) {
+            __threadfence();
+            const double total = atomicAdd(acc + b, 0.0);  // every block's sum is in
+            int present = 0;
+            for (int c = 0; c < C; ++c) present += count[(size_t)b * C + c] > 0;
+            float gsum = 1.f;  // + BG (SoftMaxAE.py:82-84)
+            for (int c = 0; c < C - 1; ++c) gsum = __fadd_rn(gsum, gt_labels[(size_t)b * (C - 1) + c]);
+            const float bw = (gsum == (float)present) ? 1.f : 0.f;
+            bw_out[b] = bw;
+            loss[b] = bw * (float)(total * inv_hw);
+        }
+    }
+}
+
 // Backward without resampling: one thread per pixel.  grid (tiles_x, tiles_y, B)
 __global__ void __launch_bounds__(LS_BX * LS_BY)
 ce_backward_same_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ label, const float* __restrict__ bw,
@@ -332,7 +463,22 @@ int launch_mask_ce_forward(const float* logits, const uint8_t* label, const int*
     if (grid.y > 65535 || grid.z > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "mask_ce: H/8 and B must be <= 65535");
     const float sh = scale_of(h, H), sw = scale_of(w, W);
     const double inv_hw = 1.0 / ((double)H * (double)W);
-    if (h != H || w != W)
+    if (H >= 2 * h && C <= CW_CB && (long long)C * h * w < (1ll << 31) && (long long)((H + 7) / 8) * W < (1ll << 30)) {
+        // enlarged logits: column walk; rows per band so that the blocks (4 per SM) fill whole waves
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) != cudaSuccess || device_sm_count(dev, &sms) != PAMR_OK || sms <= 0) sms = 148;
+        int rows = 8;
+        long long best_cost = -1;
+        for (int r = 8; r <= 32; ++r) {
+            const long long blocks = ((long long)((H + r - 1) / r) * W + CW_THREADS - 1) / CW_THREADS * B;
+            const long long cost = ((blocks + 4ll * sms - 1) / (4ll * sms)) * (r + 3);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; rows = r; }
+        }
+        const int nbands = (H + rows - 1) / rows;
+        dim3 wgrid((unsigned)((nbands * W + CW_THREADS - 1) / CW_THREADS), B);
+        ce_forward_walk_kernel<<<wgrid, CW_THREADS, 0, s>>>(logits, label, class_count, gt_labels, k.acc, k.ticket, k.bw, loss,
+                                                            k.lse, k.coef, C, h, w, H, W, sh, sw, inv_hw, rows, nbands);
+    } else if (h != H || w != W)
         ce_forward_kernel<true><<<grid, block, 0, s>>>(logits, label, class_count, gt_labels, k.acc, k.ticket, k.bw, loss, k.lse, k.coef, C, h, w, H, W, sh, sw, inv_hw);
     else
         ce_forward_kernel<false><<<grid, block, 0, s>>>(logits, label, class_count, gt_labels, k.acc, k.ticket, k.bw, loss, k.lse, k.coef, C, h, w, H, W, sh, sw, inv_hw);

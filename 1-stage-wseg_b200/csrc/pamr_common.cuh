@@ -177,6 +177,60 @@ __device__ __forceinline__ float bilerp(const float* __restrict__ pl, int w, con
 __host__ __device__ __forceinline__ float scale_of(int in_size, int out_size) {
     return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
 }
+// Column walk over an enlarged map.  bilerp() is  v = ly.l0 * t0 + ly.l1 * t1  with
+//     t0 = lx.l0 * p[i0][x0] + lx.l1 * p[i0][x1],   t1 = the same on source row i1,
+// and t0 / t1 depend on the SOURCE row only: a thread that owns one output column and walks down its rows recomputes
+// them when the source row pair changes (every k-th output row of a k-fold enlargement; the new t0 usually is the old
+// t1) and pays one FMUL/FMUL/FADD per output value otherwise.  CB planes (classes) of one image are carried together;
+// planes beyond C re-read plane C-1, so that everything over the planes is branch-free and the 2 x CB loads of a new
+// source row are in flight together.  value() is the same expression in the same order as bilerp(): bit-identical.
+template <int CB>
+struct ColumnWalk {
+    int i0, i1;  // source rows held in t0 / t1
+    float t0[CB], t1[CB];
+    __device__ __forceinline__ void reset() {
+        i0 = i1 = -1;
+#pragma unroll
+        for (int j = 0; j < CB; ++j) t0[j] = t1[j] = 0.f;
+    }
+    // x-interpolated values of source row `row` (off = row * w) of the planes pimg + min(j, C-1) * hw
+    static __device__ __forceinline__ void load_row(const float* __restrict__ pimg, int C, int hw, int off, const Lerp& lx,
+                                                    float (&tt)[CB]) {
+        float a[CB], c[CB];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+            const int o = min(j, C - 1) * hw + off;
+            a[j] = __ldg(pimg + o + lx.i0);
+            c[j] = __ldg(pimg + o + lx.i1);
+        }
+#pragma unroll
+        for (int j = 0; j < CB; ++j) tt[j] = __fadd_rn(__fmul_rn(lx.l0, a[j]), __fmul_rn(lx.l1, c[j]));
+    }
+    // make t0 / t1 the rows ly needs (C * hw < 2^31)
+    __device__ __forceinline__ void advance(const float* __restrict__ pimg, int C, int hw, int w, const Lerp& ly, const Lerp& lx) {
+        if (ly.i0 == i0 && ly.i1 == i1) return;
+        if (ly.i0 == i1) {
+#pragma unroll
+            for (int j = 0; j < CB; ++j) t0[j] = t1[j];
+        } else {
+            load_row(pimg, C, hw, ly.i0 * w, lx, t0);
+        }
+        if (ly.i1 == ly.i0) {
+#pragma unroll
+            for (int j = 0; j < CB; ++j) t1[j] = t0[j];
+        } else {
+            load_row(pimg, C, hw, ly.i1 * w, lx, t1);
+        }
+        i0 = ly.i0;
+        i1 = ly.i1;
+    }
+    __device__ __forceinline__ float value(int j, const Lerp& ly) const {
+        return __fadd_rn(__fmul_rn(ly.l0, t0[j]), __fmul_rn(ly.l1, t1[j]));
+    }
+};
+// Rows per band for the walks that carry all classes per thread (4 blocks of `threads` per SM): the candidate with the
+// cheapest schedule, waves x (rows + the loads of a band's first row pair, worth about 3 rows).
+int walk_rows(int B, int H, int W, int threads);
 #endif
 
 #ifdef __CUDACC__

@@ -57,19 +57,9 @@ clean_kernel(const float* __restrict__ m, const float* __restrict__ labels, floa
 }
 
 // ---- the resized epilogue (stage_net's real call shapes: masks 81x81 / 41x41 -> 321x321, SoftMaxAE.py:266) ----
-// Column walk: a thread owns one output column x of a band of output rows.  bilerp() is
-//     v = ly.l0 * t0 + ly.l1 * t1,   t0 = lx.l0 * p[i0][x0] + lx.l1 * p[i0][x1],   t1 = the same on row i1,
-// and t0 / t1 depend on the SOURCE row only: when the map is enlarged k times a thread recomputes them every k-th
-// output row (the new t0 usually is the old t1), and an output pixel costs 3 floating-point instructions instead
-// of 4 loads + 9.  Every value is produced by the same expression in the same order as bilerp(), so the results are
-// bit-identical to the one-thread-per-pixel kernels this replaces (0.273 -> see profiles/r02_real_shape_times.txt).
-struct RowPair {
-    int i0, i1;  // source rows currently held in t0 / t1
-};
-__device__ __forceinline__ float lerp_row(const float* __restrict__ pl, int off, const Lerp& lx) {
-    return __fadd_rn(__fmul_rn(lx.l0, __ldg(pl + off + lx.i0)), __fmul_rn(lx.l1, __ldg(pl + off + lx.i1)));
-}
-
+// Column walks (ColumnWalk, pamr_common.cuh): a thread owns one output column x of a band of output rows; an output
+// value costs 3 floating-point instructions instead of 4 loads + 9, and is bit-identical to bilerp()
+// (pseudo_labels with resize 0.273 -> 0.054 ms, profiles/r02_real_shape_times.txt).
 constexpr int CW_THREADS = 256;
 constexpr int CW_ROWS = 32;      // output rows per band in the max / store pass
 constexpr int CW_TAB = 512;      // row table: the Lerp of every output row a block touches, computed once per block
@@ -104,8 +94,8 @@ clean_walk_kernel(const float* __restrict__ m, const float* __restrict__ labels,
         const float* __restrict__ pl = m + plane * h * w;
         float* __restrict__ dst = cleaned != nullptr ? cleaned + plane * H * W + x : nullptr;
         const Lerp lx = make_lerp(x, sw, w);
-        RowPair cur{-1, -1};
-        float t0 = 0.f, t1 = 0.f;
+        ColumnWalk<1> cw;
+        cw.reset();
         for (int y = band * CW_ROWS; y < y1; ++y) {
             Lerp ly;
             if (use_tab) {
@@ -114,13 +104,8 @@ clean_walk_kernel(const float* __restrict__ m, const float* __restrict__ labels,
             } else {
                 ly = make_lerp(y, sh, h);
             }
-            if (ly.i0 != cur.i0 || ly.i1 != cur.i1) {
-                t0 = (ly.i0 == cur.i1) ? t1 : lerp_row(pl, ly.i0 * w, lx);
-                t1 = (ly.i1 == ly.i0) ? t0 : lerp_row(pl, ly.i1 * w, lx);
-                cur.i0 = ly.i0;
-                cur.i1 = ly.i1;
-            }
-            float v = __fadd_rn(__fmul_rn(ly.l0, t0), __fmul_rn(ly.l1, t1));
+            cw.advance(pl, 1, 0, w, ly, lx);
+            float v = cw.value(0, ly);
             if (gated) v = __fmul_rn(v, g);
             if (dst != nullptr) dst[(size_t)y * W] = v;
             best = max(best, ordered_from_float(v));
@@ -214,19 +199,6 @@ pseudo_labels_kernel(const float* __restrict__ m, const float* __restrict__ labe
 // blocks is full).  Everything over the classes is branch-free (classes beyond C re-read class C-1 and carry an
 // infinite threshold), so that the 2 x 21 loads of a new source row are all in flight before the first is used.
 // grid: (ceil(nbands * W / PW_THREADS), B); C * h * w < 2^31.
-__device__ __forceinline__ void lerp_row_all(const float* __restrict__ pimg, int C, int hw, int off, const Lerp& lx,
-                                             float (&tt)[PW_CB]) {
-    float a[PW_CB], c[PW_CB];
-#pragma unroll
-    for (int j = 0; j < PW_CB; ++j) {
-        const int o = min(j, C - 1) * hw + off;
-        a[j] = __ldg(pimg + o + lx.i0);
-        c[j] = __ldg(pimg + o + lx.i1);
-    }
-#pragma unroll
-    for (int j = 0; j < PW_CB; ++j) tt[j] = __fadd_rn(__fmul_rn(lx.l0, a[j]), __fmul_rn(lx.l1, c[j]));
-}
-
 // max.NaN: a NaN input gives NaN (torch.max propagates it, and so does the ordered-uint max of the other kernels)
 __device__ __forceinline__ float max_nan(float a, float b) {
     float r;
@@ -261,32 +233,14 @@ class_max_walk_kernel(const float* __restrict__ m, const float* __restrict__ lab
         const int y1 = min(H, (band + 1) * rows);
         const float* __restrict__ pimg = m + (size_t)b * C * hw;
         const Lerp lx = make_lerp(x, sw, w);
-        RowPair cur{-1, -1};
-        float t0[PW_CB], t1[PW_CB];
-#pragma unroll
-        for (int j = 0; j < PW_CB; ++j) t0[j] = t1[j] = 0.f;
+        ColumnWalk<PW_CB> cw;
+        cw.reset();
         for (int y = band * rows; y < y1; ++y) {
             const Lerp ly = make_lerp(y, sh, h);
-            if (ly.i0 != cur.i0 || ly.i1 != cur.i1) {
-                if (ly.i0 == cur.i1) {
-#pragma unroll
-                    for (int j = 0; j < PW_CB; ++j) t0[j] = t1[j];
-                } else {
-                    lerp_row_all(pimg, C, hw, ly.i0 * w, lx, t0);
-                }
-                if (ly.i1 == ly.i0) {
-#pragma unroll
-                    for (int j = 0; j < PW_CB; ++j) t1[j] = t0[j];
-                } else {
-                    lerp_row_all(pimg, C, hw, ly.i1 * w, lx, t1);
-                }
-                cur.i0 = ly.i0;
-                cur.i1 = ly.i1;
-            }
+            cw.advance(pimg, C, hw, w, ly, lx);
 #pragma unroll
             for (int j = 0; j < PW_CB; ++j) {  // gate 1 (class 0, no labels): fl(v * 1) == v
-                const float v = __fadd_rn(__fmul_rn(ly.l0, t0[j]), __fmul_rn(ly.l1, t1[j]));
-                best[j] = max_nan(best[j], __fmul_rn(v, gate[j]));
+                best[j] = max_nan(best[j], __fmul_rn(cw.value(j, ly), gate[j]));
             }
         }
     }
@@ -330,36 +284,18 @@ pseudo_labels_walk_kernel(const float* __restrict__ m, const float* __restrict__
         const int y1 = min(H, (band + 1) * rows);
         const float* __restrict__ pimg = m + (size_t)b * C * hw;
         const Lerp lx = make_lerp(x, sw, w);
-        RowPair cur{-1, -1};
-        float t0[PW_CB], t1[PW_CB];
-#pragma unroll
-        for (int j = 0; j < PW_CB; ++j) t0[j] = t1[j] = 0.f;
+        ColumnWalk<PW_CB> cw;
+        cw.reset();
         for (int y = band * rows; y < y1; ++y) {
             const Lerp ly = make_lerp(y, sh, h);
-            if (ly.i0 != cur.i0 || ly.i1 != cur.i1) {
-                if (ly.i0 == cur.i1) {
-#pragma unroll
-                    for (int j = 0; j < PW_CB; ++j) t0[j] = t1[j];
-                } else {
-                    lerp_row_all(pimg, C, hw, ly.i0 * w, lx, t0);
-                }
-                if (ly.i1 == ly.i0) {
-#pragma unroll
-                    for (int j = 0; j < PW_CB; ++j) t1[j] = t0[j];
-                } else {
-                    lerp_row_all(pimg, C, hw, ly.i1 * w, lx, t1);
-                }
-                cur.i0 = ly.i0;
-                cur.i1 = ly.i1;
-            }
+            cw.advance(pimg, C, hw, w, ly, lx);
             // x -> fl(x * 1) is the identity, so the un-gated classes (class 0, or no labels at all: gate 1) go
             // through the same multiply as the gated ones
             unsigned hits = 0u;
 #pragma unroll
             for (int j = 0; j < PW_CB; ++j) {
                 const float2 tg = thr_gate[j];
-                const float v = __fadd_rn(__fmul_rn(ly.l0, t0[j]), __fmul_rn(ly.l1, t1[j]));
-                if (__fmul_rn(v, tg.y) > tg.x) hits |= 1u << j;
+                if (__fmul_rn(cw.value(j, ly), tg.y) > tg.x) hits |= 1u << j;
             }
             const bool one = __popc(hits) == 1;
             const int first = __ffs(hits) - 1;
@@ -457,25 +393,24 @@ merge_multiscale_kernel(const float* __restrict__ masks, const MergePads pads, c
     if (pred != nullptr) pred[(size_t)y * W + x] = (uint8_t)arg;
 }
 
-// Rows per band of the all-classes walks: the candidate with the cheapest schedule, waves of 4 blocks per SM x (rows +
-// the loads of a band's first row pair, worth about 3 rows).
-int walk_rows(int B, int H, int W) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) != cudaSuccess || device_sm_count(dev, &sms) != PAMR_OK || sms <= 0) sms = 148;
-    int rows = 8;
-    long long best_cost = -1;
-    for (int r = 8; r <= 32; ++r) {
-        const long long blocks = ((long long)((H + r - 1) / r) * W + PW_THREADS - 1) / PW_THREADS * B;
-        const long long cost = ((blocks + 4ll * sms - 1) / (4ll * sms)) * (r + 3);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; rows = r; }
-    }
-    return rows;
-}
 bool walk_all_classes_ok(int B, int C, int h, int w, int H, int W) {
     return C <= PW_CB && B <= 65535 && (long long)((H + 7) / 8) * W < (1ll << 30) && (long long)C * h * w < (1ll << 31);
 }
 
 }  // namespace
+
+int walk_rows(int B, int H, int W, int threads) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || device_sm_count(dev, &sms) != PAMR_OK || sms <= 0) sms = 148;
+    int rows = 8;
+    long long best_cost = -1;
+    for (int r = 8; r <= 32; ++r) {
+        const long long blocks = ((long long)((H + r - 1) / r) * W + threads - 1) / threads * B;
+        const long long cost = ((blocks + 4ll * sms - 1) / (4ll * sms)) * (r + 3);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; rows = r; }
+    }
+    return rows;
+}
 
 int launch_resize_bilinear(const float* src, float* dst, int n_planes, int h, int w, int H, int W, cudaStream_t s) {
     if (h == H && w == W) {
@@ -514,7 +449,7 @@ int launch_clean(const float* m, const float* labels, float* cleaned, unsigned* 
         if (grid.y > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "clean: H too large");
         clean_kernel<<<grid, block, 0, s>>>(m, labels, cleaned, cls_max, C, H, W);
     } else if (cleaned == nullptr && walk_all_classes_ok(B, C, h, w, H, W)) {
-        const int rows = walk_rows(B, H, W), nbands = (H + rows - 1) / rows;
+        const int rows = walk_rows(B, H, W, PW_THREADS), nbands = (H + rows - 1) / rows;
         dim3 grid((unsigned)((nbands * W + PW_THREADS - 1) / PW_THREADS), B);
         class_max_walk_kernel<<<grid, PW_THREADS, 0, s>>>(m, labels, cls_max, C, h, w, H, W, scale_of(h, H), scale_of(w, W),
                                                           rows, nbands);
@@ -549,7 +484,7 @@ int launch_pseudo_labels(const float* m, const float* labels, const unsigned* cl
                                                                       C, h, w, H, W, 0.f, 0.f, bg_cut, fg_cut, low_cut,
                                                                       max_is_gated);
     else if (walk_all_classes_ok(B, C, h, w, H, W)) {
-        const int rows = walk_rows(B, H, W);
+        const int rows = walk_rows(B, H, W, PW_THREADS);
         const int nbands = (H + rows - 1) / rows;
         dim3 wgrid((unsigned)((nbands * W + PW_THREADS - 1) / PW_THREADS), B);
         pseudo_labels_walk_kernel<<<wgrid, PW_THREADS, 0, s>>>(m, labels, cls_max, label, pseudo_gt, class_count, C, h, w,

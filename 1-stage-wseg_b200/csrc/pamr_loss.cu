@@ -194,28 +194,15 @@ ce_forward_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ 
 }
 
 // Forward with up-sampled logits (the training shapes: logits 81x81 / 41x41, labels 321x321) as a COLUMN WALK, like
-// the resized epilogue (pamr_epilogue.cu): a thread owns one label column of a band of label rows and keeps, for all
-// C <= CW_CB classes, the x-interpolated logits of the two source rows (t0, t1 of bilerp) in registers; a label row
-// whose source row pair is unchanged costs one FMUL/FMUL/FADD per class instead of four loads and nine operations.
+// the resized epilogue (ColumnWalk, pamr_common.cuh): a thread owns one label column of a band of label rows and keeps,
+// for all C <= CW_CB classes, the x-interpolated logits of the two source rows in registers; a label row whose source
+// row pair is unchanged costs one FMUL/FMUL/FADD per class instead of four loads and nine operations.
 // Per pixel the values and the log-sum-exp recurrence are those of ce_forward_kernel (same expressions, same batches
 // of CE_BATCH classes), so lse / coef are bit-identical; only the order of the double sum differs.
 // grid (ceil(nbands * W / CW_THREADS), B); C * h * w < 2^31
 constexpr int CW_THREADS = 128;
 constexpr int CW_CB = 21;
 static_assert(CW_CB % CE_BATCH == 0, "whole batches");
-__device__ __forceinline__ void ce_row_all(const float* __restrict__ pimg, int C, int hw, int off, const Lerp& lx,
-                                           float (&tt)[CW_CB]) {
-    float a[CW_CB], c[CW_CB];
-#pragma unroll
-    for (int j = 0; j < CW_CB; ++j) {
-        const int o = min(j, C - 1) * hw + off;
-        a[j] = __ldg(pimg + o + lx.i0);
-        c[j] = __ldg(pimg + o + lx.i1);
-    }
-#pragma unroll
-    for (int j = 0; j < CW_CB; ++j) tt[j] = __fadd_rn(__fmul_rn(lx.l0, a[j]), __fmul_rn(lx.l1, c[j]));
-}
-
 __global__ void __launch_bounds__(CW_THREADS, 4)
 ce_forward_walk_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ label, const int* __restrict__ count,
                        const float* __restrict__ gt_labels, double* __restrict__ acc, unsigned* __restrict__ ticket,
@@ -243,28 +230,11 @@ ce_forward_walk_kernel(const float* __restrict__ logits, const uint8_t* __restri
         const int y1 = min(H, (band + 1) * rows);
         const float* __restrict__ pimg = logits + (size_t)b * C * hw;
         const Lerp lx = make_lerp(x, sw, w);
-        int ci0 = -1, ci1 = -1;
-        float t0[CW_CB], t1[CW_CB];
-#pragma unroll
-        for (int j = 0; j < CW_CB; ++j) t0[j] = t1[j] = 0.f;
+        ColumnWalk<CW_CB> cw;
+        cw.reset();
         for (int y = band * rows; y < y1; ++y) {
             const Lerp ly = make_lerp(y, sh, h);
-            if (ly.i0 != ci0 || ly.i1 != ci1) {
-                if (ly.i0 == ci1) {
-#pragma unroll
-                    for (int j = 0; j < CW_CB; ++j) t0[j] = t1[j];
-                } else {
-                    ce_row_all(pimg, C, hw, ly.i0 * w, lx, t0);
-                }
-                if (ly.i1 == ly.i0) {
-#pragma unroll
-                    for (int j = 0; j < CW_CB; ++j) t1[j] = t0[j];
-                } else {
-                    ce_row_all(pimg, C, hw, ly.i1 * w, lx, t1);
-                }
-                ci0 = ly.i0;
-                ci1 = ly.i1;
-            }
+            cw.advance(pimg, C, hw, w, ly, lx);
             const size_t p = (size_t)b * HW + (size_t)y * W + x;
             const int lab = label[p];
             float lse = 0.f, coef = 0.f;
@@ -275,8 +245,7 @@ ce_forward_walk_kernel(const float* __restrict__ logits, const uint8_t* __restri
                     float vb[CE_BATCH];
 #pragma unroll
                     for (int j = 0; j < CE_BATCH; ++j) {  // classes beyond C: -inf, which leaves the maximum and the sum alone
-                        const float z = __fadd_rn(__fmul_rn(ly.l0, t0[c0 + j]), __fmul_rn(ly.l1, t1[c0 + j]));
-                        vb[j] = (c0 + j < C) ? z : -INFINITY;
+                        vb[j] = (c0 + j < C) ? cw.value(c0 + j, ly) : -INFINITY;
                     }
                     float bm = vb[0];
 #pragma unroll
@@ -465,15 +434,7 @@ int launch_mask_ce_forward(const float* logits, const uint8_t* label, const int*
     const double inv_hw = 1.0 / ((double)H * (double)W);
     if (H >= 2 * h && C <= CW_CB && (long long)C * h * w < (1ll << 31) && (long long)((H + 7) / 8) * W < (1ll << 30)) {
         // enlarged logits: column walk; rows per band so that the blocks (4 per SM) fill whole waves
-        int dev = 0, sms = 148;
-        if (cudaGetDevice(&dev) != cudaSuccess || device_sm_count(dev, &sms) != PAMR_OK || sms <= 0) sms = 148;
-        int rows = 8;
-        long long best_cost = -1;
-        for (int r = 8; r <= 32; ++r) {
-            const long long blocks = ((long long)((H + r - 1) / r) * W + CW_THREADS - 1) / CW_THREADS * B;
-            const long long cost = ((blocks + 4ll * sms - 1) / (4ll * sms)) * (r + 3);
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; rows = r; }
-        }
+        const int rows = walk_rows(B, H, W, CW_THREADS);
         const int nbands = (H + rows - 1) / rows;
         dim3 wgrid((unsigned)((nbands * W + CW_THREADS - 1) / CW_THREADS), B);
         ce_forward_walk_kernel<<<wgrid, CW_THREADS, 0, s>>>(logits, label, class_count, gt_labels, k.acc, k.ticket, k.bw, loss,

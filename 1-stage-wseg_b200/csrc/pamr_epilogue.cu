@@ -206,13 +206,15 @@ __device__ __forceinline__ float max_nan(float a, float b) {
     return r;
 }
 
-// The max pass of the resized epilogue for C <= PW_CB classes when the cleaned masks are not wanted: same walk as the
-// label pass below (one thread, all classes of a column band), a running maximum per class in registers, one
-// atomicMax per class and block.  One class per thread (clean_walk_kernel) pays the row bookkeeping per class: 56 us
-// against the 28 us of the label pass for the same values.  grid: (ceil(nbands * W / PW_THREADS), B)
+// The max pass of the resized epilogue for C <= PW_CB classes (_rescale_and_clean at a new size, SoftMaxAE.py:263-268,
+// with the cleaned masks stored on request): same walk as the label pass below (one thread, all classes of a column
+// band), a running maximum per class in registers, one atomicMax per class and block.  One class per thread
+// (clean_walk_kernel, kept for more classes and for the plain resize) pays the row bookkeeping per class: 56 us
+// against the 27 us of this kernel for the same values.  grid: (ceil(nbands * W / PW_THREADS), B)
 __global__ void __launch_bounds__(PW_THREADS, 4)
-class_max_walk_kernel(const float* __restrict__ m, const float* __restrict__ labels, unsigned* __restrict__ cls_max, int C,
-                      int h, int w, int H, int W, float sh, float sw, int rows, int nbands) {
+class_max_walk_kernel(const float* __restrict__ m, const float* __restrict__ labels, float* __restrict__ cleaned,
+                      unsigned* __restrict__ cls_max, int C, int h, int w, int H, int W, float sh, float sw, int rows,
+                      int nbands) {
     __shared__ float gate[PW_CB];
     __shared__ unsigned red[PW_CB];
     const int b = blockIdx.y;
@@ -223,6 +225,7 @@ class_max_walk_kernel(const float* __restrict__ m, const float* __restrict__ lab
     }
     __syncthreads();
     const int hw = h * w;
+    const size_t HW = (size_t)H * W;
     const int t = blockIdx.x * PW_THREADS + threadIdx.x;
     const bool valid = t < nbands * W;
     float best[PW_CB];
@@ -238,12 +241,16 @@ class_max_walk_kernel(const float* __restrict__ m, const float* __restrict__ lab
         for (int y = band * rows; y < y1; ++y) {
             const Lerp ly = make_lerp(y, sh, h);
             cw.advance(pimg, C, hw, w, ly, lx);
+            float* __restrict__ dst = cleaned != nullptr ? cleaned + (size_t)b * C * HW + (size_t)y * W + x : nullptr;
 #pragma unroll
             for (int j = 0; j < PW_CB; ++j) {  // gate 1 (class 0, no labels): fl(v * 1) == v
-                best[j] = max_nan(best[j], __fmul_rn(cw.value(j, ly), gate[j]));
+                const float v = __fmul_rn(cw.value(j, ly), gate[j]);
+                if (dst != nullptr && j < C) dst[(size_t)j * HW] = v;
+                best[j] = max_nan(best[j], v);
             }
         }
     }
+    if (cls_max == nullptr) return;
 #pragma unroll
     for (int j = 0; j < PW_CB; ++j) {
         const unsigned u = __reduce_max_sync(0xffffffffu, valid ? ordered_from_float(best[j]) : 0u);
@@ -448,11 +455,11 @@ int launch_clean(const float* m, const float* labels, float* cleaned, unsigned* 
         dim3 grid((W + EP_BX - 1) / EP_BX, (H + EP_BY - 1) / EP_BY, B * C);
         if (grid.y > 65535) return set_error(PAMR_ERR_INVALID_ARGUMENT, "clean: H too large");
         clean_kernel<<<grid, block, 0, s>>>(m, labels, cleaned, cls_max, C, H, W);
-    } else if (cleaned == nullptr && walk_all_classes_ok(B, C, h, w, H, W)) {
+    } else if (walk_all_classes_ok(B, C, h, w, H, W)) {
         const int rows = walk_rows(B, H, W, PW_THREADS), nbands = (H + rows - 1) / rows;
         dim3 grid((unsigned)((nbands * W + PW_THREADS - 1) / PW_THREADS), B);
-        class_max_walk_kernel<<<grid, PW_THREADS, 0, s>>>(m, labels, cls_max, C, h, w, H, W, scale_of(h, H), scale_of(w, W),
-                                                          rows, nbands);
+        class_max_walk_kernel<<<grid, PW_THREADS, 0, s>>>(m, labels, cleaned, cls_max, C, h, w, H, W, scale_of(h, H),
+                                                          scale_of(w, W), rows, nbands);
     } else {
         const int nbands = (H + CW_ROWS - 1) / CW_ROWS;
         if ((long long)nbands * W >= (1ll << 30) || (long long)h * w >= (1ll << 31))

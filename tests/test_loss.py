@@ -107,7 +107,8 @@ def test_gpu_loss_vs_reference_golden(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dims", [(2, 21, 41, 41, 161, 161), (3, 21, 33, 37, 33, 37), (2, 5, 50, 40, 17, 13),
-                                  (1, 2, 1, 1, 9, 7), (2, 40, 11, 13, 40, 45), (4, 21, 81, 81, 321, 321)])
+                                  (1, 2, 1, 1, 9, 7), (2, 40, 11, 13, 40, 45), (4, 21, 81, 81, 321, 321),
+                                  (2, 7, 20, 30, 97, 65), (1, 21, 8, 40, 33, 40), (2, 21, 16, 9, 40, 8)])
 def test_gpu_loss_vs_oracle(dims):
     B, C, h, w, H, W = dims
     logits, pg, lab, gl, gout = _random_case(11 + h, B, C, h, w, H, W)

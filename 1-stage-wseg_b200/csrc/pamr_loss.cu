@@ -35,7 +35,7 @@ struct CeWorkspace {
     float* bw;       // [B]    batch weight (written by the forward pass)
     float* lse;      // [B,H,W]
     float* coef;     // [B,H,W]
-    float* T;        // [B,C,H,w]  backward with resampling: the gradient after the x pass
+    float* T;        // backward with resampling: the gradient after the first pass, [B,C,H,w] (x first) or [B,C,h,W] (y first)
     size_t head_bytes;  // acc + ticket: zeroed by one memset before the forward kernel
 };
 __host__ __device__ inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
@@ -232,11 +232,17 @@ ce_forward_walk_kernel(const float* __restrict__ logits, const uint8_t* __restri
         const Lerp lx = make_lerp(x, sw, w);
         ColumnWalk<CW_CB> cw;
         cw.reset();
+        const size_t col = (size_t)b * HW + x;
+        int plab[2];  // the label is fetched two rows ahead (a dependent round trip to L2 per row otherwise)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) plab[k] = (band * rows + k < y1) ? (int)label[col + (size_t)(band * rows + k) * W] : 255;
         for (int y = band * rows; y < y1; ++y) {
             const Lerp ly = make_lerp(y, sh, h);
             cw.advance(pimg, C, hw, w, ly, lx);
-            const size_t p = (size_t)b * HW + (size_t)y * W + x;
-            const int lab = label[p];
+            const size_t p = col + (size_t)y * W;
+            const int lab = plab[0];
+            plab[0] = plab[1];
+            if (y + 2 < y1) plab[1] = label[col + (size_t)(y + 2) * W];
             float lse = 0.f, coef = 0.f;
             if (lab < C) {
                 float m = -INFINITY, s = 0.f, zl = 0.f;
@@ -399,10 +405,135 @@ ce_backward_ypass_kernel(const float* __restrict__ T, const float* __restrict__ 
     grad[(size_t)plane * h * w + (size_t)i * w + j] = g * acc;
 }
 
+// ---- backward with ENLARGED logits (H >= 2h: the training shapes), y first ----
+//   U[b,c,i,x]    = sum_y coef(y,x) * (softmax_c(y,x) - [c == label(y,x)]) * wy(y -> i)      (logit rows, label columns)
+//   grad[b,c,i,j] = g_b * bw_b * sum_x U[b,c,i,x] * wx(x -> j)
+// The first pass is a column walk (ColumnWalk, pamr_common.cuh) like the forward pass: a thread owns one label
+// column x, BA_CB classes and a band of `srows` logit rows; it walks down the label rows whose source row pair
+// touches its band, computes each pixel's softmax term ONCE (the x-first order above evaluates it for both logit
+// columns a pixel feeds, and re-interpolates the logits per pixel) from the same z as the forward pass, and adds
+// wy.l0 * G to the accumulator of logit row i0 and wy.l1 * G to that of row i1, both in registers; a row's sum is
+// stored when the walk leaves it.  Deterministic without atomics: every U element has one owner, which also walks
+// the label rows just above its band (their i1 is the band's first row) -- (srows + 1) / srows of the work; the launcher
+// picks srows so that the blocks (4 per SM) fill whole waves.
+constexpr int BA_THREADS = 128;
+constexpr int BA_CB = 11;  // classes per thread (21 = 11 + 10; with 21 the four register arrays spill): the per-pixel bookkeeping is paid per batch
+
+// grid (ceil(nbands * W / BA_THREADS), ceil(C / BA_CB), B), nbands = ceil(h / srows); BA_CB * h * w < 2^31
+__global__ void __launch_bounds__(BA_THREADS, 4)
+ce_backward_ywalk_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ label, const float* __restrict__ lse_in,
+                         const float* __restrict__ coef_in, float* __restrict__ U, int C, int h, int w, int H, int W, float sh,
+                         float sw, int srows, int nbands) {
+    const int t = blockIdx.x * BA_THREADS + threadIdx.x;
+    if (t >= nbands * W) return;
+    const int band = t / W, x = t - band * W;
+    const int c0 = blockIdx.y * BA_CB, b = blockIdx.z, nc = min(BA_CB, C - c0);
+    const int ia = band * srows, ib = min(h, ia + srows);  // logit rows this thread owns
+    const int hw = h * w;
+    const size_t HW = (size_t)H * W;
+    const float* __restrict__ pimg = logits + ((size_t)b * C + c0) * hw;
+    float* __restrict__ ub = U + ((size_t)b * C + c0) * h * W + x;
+    const Lerp lx = make_lerp(x, sw, w);
+    ColumnWalk<BA_CB> cw;
+    cw.reset();
+    float acc0[BA_CB], acc1[BA_CB];  // sums of logit rows r0 / r1
+#pragma unroll
+    for (int q = 0; q < BA_CB; ++q) acc0[q] = acc1[q] = 0.f;
+    int r0 = -1, r1 = -1;
+    // row r of the band is complete: store it (r0 == r1 on the last logit row: both accumulators are that row's)
+    auto store_row = [&](int r, const float (&a)[BA_CB], const float (&a2)[BA_CB], bool both) {
+        if (r < ia || r >= ib) return;
+#pragma unroll
+        for (int q = 0; q < BA_CB; ++q)
+            if (q < nc) ub[((size_t)q * h + r) * W] = both ? a[q] + a2[q] : a[q];
+    };
+    // first label row whose source row pair reaches row ia (its i1 >= ia); the estimate is low by construction
+    int y = (sh > 0.f && ia > 0) ? max(0, (int)((float)(ia - 1) / sh) - 1) : 0;
+    while (y < H && make_lerp(y, sh, h).i1 < ia) ++y;
+    // the per-pixel inputs (coef, lse, label) are fetched two label rows ahead: read where they are used, every row
+    // would wait for two dependent round trips to L2 (89 us instead of the time below)
+    const size_t col = (size_t)b * HW + x;
+    float pc[2] = {0.f, 0.f}, pl[2] = {0.f, 0.f};
+    int plab[2] = {255, 255};
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (y + k < H) {
+            const size_t p = col + (size_t)(y + k) * W;
+            pc[k] = __ldg(coef_in + p); pl[k] = __ldg(lse_in + p); plab[k] = label[p];
+        }
+    for (; y < H; ++y) {
+        const Lerp ly = make_lerp(y, sh, h);
+        if (ly.i0 >= ib) break;
+        const float coef = pc[0], lse = pl[0];
+        const int lab = plab[0] - c0;
+        pc[0] = pc[1]; pl[0] = pl[1]; plab[0] = plab[1];
+        if (y + 2 < H) {
+            const size_t p = col + (size_t)(y + 2) * W;
+            pc[1] = __ldg(coef_in + p); pl[1] = __ldg(lse_in + p); plab[1] = label[p];
+        }
+        if (ly.i0 != r0 || ly.i1 != r1) {
+            if (r0 >= 0) {
+                if (ly.i0 == r1 && r1 != r0) {  // the pair moved down by one row: r0 is complete, r1 carries on as the upper row
+                    store_row(r0, acc0, acc1, false);
+#pragma unroll
+                    for (int q = 0; q < BA_CB; ++q) { acc0[q] = acc1[q]; acc1[q] = 0.f; }
+                } else {  // any other move (not produced by an enlargement): both rows are complete
+                    store_row(r0, acc0, acc1, r1 == r0);
+                    if (r1 != r0) store_row(r1, acc1, acc0, false);
+#pragma unroll
+                    for (int q = 0; q < BA_CB; ++q) acc0[q] = acc1[q] = 0.f;
+                }
+            }
+            r0 = ly.i0;
+            r1 = ly.i1;
+        }
+        cw.advance(pimg, nc, hw, w, ly, lx);
+        if (coef != 0.f) {
+            const float nl = -lse * CE_LOG2E;
+#pragma unroll
+            for (int q = 0; q < BA_CB; ++q) {
+                const float gq = coef * (ce_ex2(fmaf(cw.value(q, ly), CE_LOG2E, nl)) - (lab == q ? 1.f : 0.f));
+                acc0[q] = fmaf(ly.l0, gq, acc0[q]);
+                acc1[q] = fmaf(ly.l1, gq, acc1[q]);
+            }
+        }
+    }
+    if (r0 >= 0) {
+        store_row(r0, acc0, acc1, r1 == r0);
+        if (r1 != r0) store_row(r1, acc1, acc0, false);
+    }
+}
+
+// x pass of the y-first order: grad[b,c,i,j] = g_b * bw_b * sum_x U[b,c,i,x] * wx(x -> j).  grid (ceil(w/32), ceil(h/8), B*C)
+__global__ void __launch_bounds__(LS_BX * LS_BY)
+ce_backward_xgather_kernel(const float* __restrict__ U, const float* __restrict__ bw, const float* __restrict__ gout,
+                           float* __restrict__ grad, int C, int h, int w, int W, float sw) {
+    const int j = blockIdx.x * LS_BX + threadIdx.x, i = blockIdx.y * LS_BY + threadIdx.y;
+    const int plane = blockIdx.z, b = plane / C;
+    if (j >= w || i >= h) return;
+    const float g = gout[b] * bw[b];
+    float acc = 0.f;
+    if (g != 0.f) {
+        int xlo, xhi;
+        footprint(j, sw, W, xlo, xhi);
+        const float* __restrict__ up = U + ((size_t)plane * h + i) * W;
+        for (int x = xlo; x <= xhi; ++x) {
+            const float wx = weight_to(make_lerp(x, sw, w), j);
+            if (wx != 0.f) acc = fmaf(wx, __ldg(up + x), acc);
+        }
+    }
+    grad[(size_t)plane * h * w + (size_t)i * w + j] = g * acc;
+}
+
+// the y-first backward applies (the same predicate sizes the workspace)
+inline bool backward_y_first(int h, int w, int H) { return H >= 2 * h && (long long)BA_CB * h * w < (1ll << 31); }
+
 }  // namespace
 
 size_t mask_ce_workspace_bytes(int B, int C, int h, int w, int H, int W) {
-    const size_t t_bytes = (h != H || w != W) ? up256(sizeof(float) * (size_t)B * C * H * w) : 0;
+    // intermediate of the backward pass with resampling: T [B,C,H,w] (x first) or U [B,C,h,W] (y first)
+    const size_t t_elems = backward_y_first(h, w, H) ? (size_t)h * W : (size_t)H * w;
+    const size_t t_bytes = (h != H || w != W) ? up256(sizeof(float) * (size_t)B * C * t_elems) : 0;
     return up256(sizeof(double) * B) + up256(sizeof(unsigned) * B) + up256(sizeof(float) * B) +
            2 * up256(sizeof(float) * (size_t)B * H * W) + t_bytes;
 }
@@ -464,6 +595,30 @@ int launch_mask_ce_backward(const float* logits, const uint8_t* label, const flo
         return PAMR_OK;
     }
     const float sh = scale_of(h, H), sw = scale_of(w, W);
+    int srows = 4;
+    {   // logit rows per band: waves of 4 blocks per SM x (srows + 1)
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) != cudaSuccess || device_sm_count(dev, &sms) != PAMR_OK || sms <= 0) sms = 148;
+        long long best_cost = -1;
+        for (int r = 4; r <= 16; ++r) {
+            const long long blocks = ((long long)((h + r - 1) / r) * W + BA_THREADS - 1) / BA_THREADS * ((C + BA_CB - 1) / BA_CB) * B;
+            const long long cost = ((blocks + 4ll * sms - 1) / (4ll * sms)) * (r + 1);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; srows = r; }
+        }
+    }
+    const int nbands = (h + srows - 1) / srows;
+    if (backward_y_first(h, w, H) && (long long)nbands * W < (1ll << 30) && B <= 65535 && (size_t)B * C <= 65535 &&
+        (h + LS_BY - 1) / LS_BY <= 65535) {
+        dim3 ga((unsigned)((nbands * W + BA_THREADS - 1) / BA_THREADS), (C + BA_CB - 1) / BA_CB, B);
+        ce_backward_ywalk_kernel<<<ga, BA_THREADS, 0, s>>>(logits, label, k.lse, k.coef, k.T, C, h, w, H, W, sh, sw, srows, nbands);
+        count_launch();
+        PAMR_CUDA_TRY(cudaGetLastError());
+        dim3 gb((w + LS_BX - 1) / LS_BX, (h + LS_BY - 1) / LS_BY, B * C);
+        ce_backward_xgather_kernel<<<gb, block, 0, s>>>(k.T, k.bw, grad_loss, grad_logits, C, h, w, W, sw);
+        count_launch();
+        PAMR_CUDA_TRY(cudaGetLastError());
+        return PAMR_OK;
+    }
     dim3 gx((w + LS_BX - 1) / LS_BX, (H + LS_BY - 1) / LS_BY, B * ((C + CE_BATCH - 1) / CE_BATCH));
     dim3 gy((w + LS_BX - 1) / LS_BX, (h + LS_BY - 1) / LS_BY, B * C);
     if (gx.y > 65535 || gy.y > 65535 || gy.z > 65535)

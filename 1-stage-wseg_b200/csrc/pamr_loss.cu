@@ -505,21 +505,31 @@ ce_backward_ywalk_kernel(const float* __restrict__ logits, const uint8_t* __rest
 }
 
 // x pass of the y-first order: grad[b,c,i,j] = g_b * bw_b * sum_x U[b,c,i,x] * wx(x -> j).  grid (ceil(w/32), ceil(h/8), B*C)
+// The weights wx(x -> j) of a logit column's footprint depend on j only: with kTab the block computes them once into
+// shared memory (row pitch 25: conflict-free) instead of every thread re-deriving make_lerp for each of its ~2/scale
+// pixels (40 us -> see profiles/r02_loss_times.txt); spans above XG_SPAN (scale < ~0.1) take the direct form.
+constexpr int XG_SPAN = 24;
+template <bool kTab>
 __global__ void __launch_bounds__(LS_BX * LS_BY)
 ce_backward_xgather_kernel(const float* __restrict__ U, const float* __restrict__ bw, const float* __restrict__ gout,
                            float* __restrict__ grad, int C, int h, int w, int W, float sw) {
+    __shared__ float wt[LS_BX][XG_SPAN + 1];
     const int j = blockIdx.x * LS_BX + threadIdx.x, i = blockIdx.y * LS_BY + threadIdx.y;
     const int plane = blockIdx.z, b = plane / C;
+    int xlo = 0, xhi = -1;
+    if (j < w) footprint(j, sw, W, xlo, xhi);
+    if (kTab) {
+        for (int k = threadIdx.y; k <= xhi - xlo; k += LS_BY) wt[threadIdx.x][k] = weight_to(make_lerp(xlo + k, sw, w), j);
+        __syncthreads();
+    }
     if (j >= w || i >= h) return;
     const float g = gout[b] * bw[b];
     float acc = 0.f;
     if (g != 0.f) {
-        int xlo, xhi;
-        footprint(j, sw, W, xlo, xhi);
-        const float* __restrict__ up = U + ((size_t)plane * h + i) * W;
-        for (int x = xlo; x <= xhi; ++x) {
-            const float wx = weight_to(make_lerp(x, sw, w), j);
-            if (wx != 0.f) acc = fmaf(wx, __ldg(up + x), acc);
+        const float* __restrict__ up = U + ((size_t)plane * h + i) * W + xlo;
+        for (int k = 0; k <= xhi - xlo; ++k) {
+            const float wx = kTab ? wt[threadIdx.x][k] : weight_to(make_lerp(xlo + k, sw, w), j);
+            if (wx != 0.f) acc = fmaf(wx, __ldg(up + k), acc);
         }
     }
     grad[(size_t)plane * h * w + (size_t)i * w + j] = g * acc;
@@ -614,7 +624,12 @@ int launch_mask_ce_backward(const float* logits, const uint8_t* label, const flo
         count_launch();
         PAMR_CUDA_TRY(cudaGetLastError());
         dim3 gb((w + LS_BX - 1) / LS_BX, (h + LS_BY - 1) / LS_BY, B * C);
-        ce_backward_xgather_kernel<<<gb, block, 0, s>>>(k.T, k.bw, grad_loss, grad_logits, C, h, w, W, sw);
+        // widest footprint of a logit column (footprint(): floor((j-1)/sw) - 1 .. ceil((j+1)/sw) + 1, clipped to the row)
+        const bool tab = sw > 0.f && 2.f / sw + 5.f <= (float)XG_SPAN;
+        if (tab)
+            ce_backward_xgather_kernel<true><<<gb, block, 0, s>>>(k.T, k.bw, grad_loss, grad_logits, C, h, w, W, sw);
+        else
+            ce_backward_xgather_kernel<false><<<gb, block, 0, s>>>(k.T, k.bw, grad_loss, grad_logits, C, h, w, W, sw);
         count_launch();
         PAMR_CUDA_TRY(cudaGetLastError());
         return PAMR_OK;

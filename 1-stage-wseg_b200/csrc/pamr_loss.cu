@@ -6,20 +6,23 @@
 //   loss[b] = bw[b] * mean_px( cw[b,label] * (logsumexp_c z - z[label]) )           (:77, :86)
 // and d(sum_b g[b] loss[b]) / d logits through the transpose of the interpolation.
 //
-// Forward (one launch + one small memset): one thread per label pixel; the C interpolated logits go through an
-// online log-sum-exp in base 2 (ex2.approx, 2 ulp); the class weights come from the counts (per block, in shared
-// memory); per-image sum in double (warp shuffle -> block -> one atomicAdd(double) per block) and the block that
-// arrives last at the image's ticket writes loss[b].  lse(px) and coef(px) = cw[label]/(H*W) (0 where ignored) stay
-// in the workspace for the backward pass.
+// Forward (one launch + one small memset): the C interpolated logits of a label pixel go through an online
+// log-sum-exp in base 2 (ex2.approx, 2 ulp); the class weights come from the counts (per block, in shared memory);
+// per-image sum in double (warp shuffle -> block -> one atomicAdd(double) per block) and the block that arrives last
+// at the image's ticket writes loss[b].  lse(px) and coef(px) = cw[label]/(H*W) (0 where ignored) stay in the
+// workspace for the backward pass.  One thread per label pixel (ce_forward_kernel), or -- logits enlarged at least
+// 2x, the training shapes -- a column walk over the label rows (ce_forward_walk_kernel).
 // Backward, deterministic, no atomics:
 //   same resolution:  one thread per pixel, grad_c = g * coef * (2^((z_c - lse) log2 e) - [c == label]);
-//   with up-/down-sampling: the transposed bilinear interpolation is separable, so it runs as two gathers --
-//     T[b,c,y,j]    = sum_x coef(y,x) * (softmax_c(y,x) - [c == label(y,x)]) * wx(x -> j)      (label rows, logit columns)
-//     grad[b,c,i,j] = g_b * sum_y T[b,c,y,j] * wy(y -> i)
-//   the first with the six logits a thread needs held in registers (its source column and the two next to it, on the
-//   two source rows of label row y), so that the inner loop over the ~2/scale pixels of its footprint has no
-//   dependent loads.  (Round 1 visited the whole 2-D footprint per logit element and recomputed bilerp + expf for
-//   each of its ~(2/scale)^2 pixels: 0.55 ms at 81x81 -> 321x321.)
+//   with resampling the transposed bilinear interpolation is separable and runs as two passes:
+//   * logits enlarged at least 2x: y first (ce_backward_ywalk_kernel, ce_backward_xgather_kernel, described there);
+//   * otherwise x first, two gathers --
+//       T[b,c,y,j]    = sum_x coef(y,x) * (softmax_c(y,x) - [c == label(y,x)]) * wx(x -> j)    (label rows, logit columns)
+//       grad[b,c,i,j] = g_b * sum_y T[b,c,y,j] * wy(y -> i)
+//     the first with the six logits a thread needs held in registers (its source column and the two next to it, on
+//     the two source rows of label row y), so that the inner loop over the ~2/scale pixels of its footprint has no
+//     dependent loads.  (Round 1 visited the whole 2-D footprint per logit element and recomputed bilerp + expf for
+//     each of its ~(2/scale)^2 pixels: 0.55 ms at 81x81 -> 321x321.)
 #include "pamr_common.cuh"
 
 namespace pamr {

@@ -252,3 +252,17 @@ def test_bench_reference_arm_line():
         assert d["config"]["sample_batch"] == gpus and "B=%d per step" % gpus in d["config"]["workload"]
         assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         assert d["gpu_launches"] == 0
+
+
+def test_mask_ce_workspace_covers_both_backward_orders():
+    """The loss workspace holds lse + coef [B,H,W] and the backward pass's intermediate, which is [B,C,H,w] (x first)
+    or [B,C,h,W] (y first, logits enlarged >= 2x): a host-only query, no device needed."""
+    from wseg_b200 import _lib
+    L = _lib.lib()
+    for (B, C, h, w, H, W) in [(16, 21, 81, 81, 321, 321), (2, 21, 8, 40, 33, 40), (2, 21, 16, 9, 40, 8), (2, 5, 50, 40, 17, 13),
+                               (3, 7, 10, 100, 20, 10)]:
+        need = L.pamr_mask_ce_workspace_bytes(B, C, h, w, H, W)
+        inter = 4 * B * C * (h * W if H >= 2 * h else H * w)
+        assert need >= 2 * 4 * B * H * W + inter
+        assert need <= 2 * 4 * B * H * W + inter + 8 * 256 + 16 * B
+    assert L.pamr_mask_ce_workspace_bytes(4, 21, 33, 37, 33, 37) < 2 * 4 * 4 * 33 * 37 + 8 * 256 + 16 * 4 + 1  # same size: no intermediate

@@ -12,7 +12,8 @@ affinity kernel of step i+1.  Rank 0 prints ONE JSON line; besides the headline 
   roofline        the propagation launch against the measured HBM peak (+ the binding on-chip roof, from ncu)
   e2e             the same step from pinned HOST buffers through HostPipeline (H2D + D2H inside the timed region)
   e2e_real_shape  the shape stage_net really calls it with: masks at 81x81 uploaded, up-sampling on the device
-  small_map       PAMR.forward at stage_net's mask sizes (the resident kernel: one launch for all iterations)
+  small_map       PAMR.forward at stage_net's mask sizes (the resident kernel: one launch for all iterations) and the
+                  whole stage step with masks of that size (ms_stage_step: image down, PAMR, clean + labels at 321x321)
   configs         BASELINE.json configs[2], [3] and [4]-on-one-GPU (N = 1 only)
   strong          configs[4] as stated: B=128 in total, split over the N GPUs
   allgather       the NCCL gather alone (N > 1)
@@ -374,9 +375,12 @@ def main():
         for hw in (41, 81):
             im_s, mk_s, _ = synth_inputs(B, hw, hw, hw, hw, 777 + hw)
             ms_s, l_s = timed(lambda: pamr(im_s, mk_s), max(20, nrep), 5)
+            # the whole stage step at this mask size: image down, PAMR, up-sampling + clean + labels at the image size
+            ms_st, _ = timed(lambda: step(image, mk_s, labels), max(20, nrep), 5)
             small.append({"shape": "B=%d %dx%d, %d classes, %d iterations" % (B, hw, hw, C, ITERS), "ms_forward": ms_s,
                           "launches_per_forward": l_s / max(20, nrep), "mpix_s": B * hw * hw / (ms_s * 1e-3) / 1e6,
-                          "whole_forward_GBps": (step_bytes_per_pixel() - 4 * C - 1) * B * hw * hw / (ms_s * 1e-3) / 1e9})
+                          "whole_forward_GBps": (step_bytes_per_pixel() - 4 * C - 1) * B * hw * hw / (ms_s * 1e-3) / 1e9,
+                          "ms_stage_step": ms_st})
             del im_s, mk_s
         extras["small_map"] = small
 
